@@ -1,0 +1,426 @@
+// Device-side game engines on 64-bit bitboards: Othello, Hex, Hex-with-swap, tic-tac-toe.
+//
+// Replaces (reference paths relative to deep_mcts/):
+//   othello/game.py:38-141, hex/game.py:37-142, hex_with_swap/game.py:16-36,
+//   tictactoe/game.py:28-97
+// and the CPython-set child ordering that mcts.py:200-215 inherits from
+// `set(legal_actions(state))` (model: SURVEY.md Appendix A).
+//
+// All functions are written to be executed warp-uniformly (every lane holds the same
+// state); the two that use lanes cooperatively say so.
+#pragma once
+#include "common.cuh"
+
+struct GameCfg {
+    int game;         // dm_game
+    int g;            // board side
+    int cells;        // g*g
+    int num_actions;  // cells (+1 pass / swap)
+    u64 full;         // all cells
+    u64 not_col0;     // cells with x != 0
+    u64 not_colL;     // cells with x != g-1
+    u64 row0, rowL, col0, colL;
+};
+
+static inline GameCfg make_game_cfg(int game, int grid) {
+    GameCfg c;
+    c.game = game;
+    c.g = (game == DM_TICTACTOE) ? 3 : grid;
+    c.cells = c.g * c.g;
+    c.num_actions = c.cells + ((game == DM_HEX_SWAP || game == DM_OTHELLO) ? 1 : 0);
+    c.full = (c.cells == 64) ? ~0ull : ((1ull << c.cells) - 1);
+    u64 col0 = 0;
+    for (int y = 0; y < c.g; ++y) col0 |= 1ull << (y * c.g);
+    c.col0 = col0;
+    c.colL = col0 << (c.g - 1);
+    c.not_col0 = c.full & ~c.col0;
+    c.not_colL = c.full & ~c.colL;
+    c.row0 = (1ull << c.g) - 1;
+    c.rowL = c.row0 << (c.g * (c.g - 1));
+    return c;
+}
+
+static inline bool game_cfg_valid(int game, int grid) {
+    switch (game) {
+        case DM_TICTACTOE: return true;
+        case DM_HEX:
+        case DM_HEX_SWAP: return grid >= 2 && grid <= 8;
+        case DM_OTHELLO: return grid >= 4 && grid <= 8 && (grid % 2 == 0);
+        default: return false;
+    }
+}
+
+struct GState {
+    u64 first, second;
+    int player;  // 1 FIRST, 0 SECOND
+};
+
+// itertools.product([0, 1, -1], repeat=2) without (0,0), as (dx, dy)  (othello/game.py:57, 89)
+#define DM_FOR_EACH_OTHELLO_DIR(F) F(0, 1) F(0, -1) F(1, 0) F(1, 1) F(1, -1) F(-1, 0) F(-1, 1) F(-1, -1)
+
+template <int DX, int DY>
+__device__ __forceinline__ u64 bb_shift(u64 b, const GameCfg& c) {
+    u64 r;
+    if (DY > 0 || (DY == 0 && DX > 0)) r = (b << (DY * c.g + DX)) & c.full;
+    else r = b >> (-(DY * c.g + DX));
+    if (DX > 0) r &= c.not_col0;
+    else if (DX < 0) r &= c.not_colL;
+    return r;
+}
+
+// ------------------------------------------------------------------------------ othello
+template <int DX, int DY>
+__device__ __forceinline__ u64 othello_moves_dir(u64 own, u64 opp, u64 empty, const GameCfg& c) {
+    u64 t = bb_shift<DX, DY>(own, c) & opp;
+    for (int i = 0; i < c.g - 3; ++i) t |= bb_shift<DX, DY>(t, c) & opp;
+    return bb_shift<DX, DY>(t, c) & empty;
+}
+
+__device__ __forceinline__ u64 othello_moves(u64 own, u64 opp, const GameCfg& c) {
+    u64 empty = ~(own | opp) & c.full;
+    u64 moves = 0;
+#define DM_DIR(DX, DY) moves |= othello_moves_dir<DX, DY>(own, opp, empty, c);
+    DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
+#undef DM_DIR
+    return moves;
+}
+
+template <int DX, int DY>
+__device__ __forceinline__ u64 othello_flips_dir(u64 own, u64 opp, u64 bit, const GameCfg& c) {
+    u64 f = bb_shift<DX, DY>(bit, c);
+    u64 run = 0;
+    while (f & opp) {
+        run |= f;
+        f = bb_shift<DX, DY>(f, c);
+    }
+    return (f & own) ? run : 0ull;
+}
+
+// stones flipped by playing `bit` (othello/game.py:56-81)
+__device__ __forceinline__ u64 othello_flips(u64 own, u64 opp, u64 bit, const GameCfg& c) {
+    u64 flips = 0;
+#define DM_DIR(DX, DY) flips |= othello_flips_dir<DX, DY>(own, opp, bit, c);
+    DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
+#undef DM_DIR
+    return flips;
+}
+
+// the empty square an own stone `bit` reaches over >=1 opponent stones in one direction,
+// else 0 (one iteration of the scan at othello/game.py:90-115)
+template <int DX, int DY>
+__device__ __forceinline__ u64 othello_ray_target(u64 own, u64 opp, u64 bit, const GameCfg& c) {
+    u64 f = bb_shift<DX, DY>(bit, c);
+    if (!(f & opp)) return 0;
+    while (f & opp) f = bb_shift<DX, DY>(f, c);
+    return f & ~(own | opp);
+}
+
+// ---------------------------------------------------------------------------------- hex
+__device__ __forceinline__ u64 hex_neighbours(u64 r, const GameCfg& c) {
+    // hex/game.py:131: (0,-1),(1,-1),(1,0),(0,1),(-1,1),(-1,0)
+    return bb_shift<0, -1>(r, c) | bb_shift<1, -1>(r, c) | bb_shift<1, 0>(r, c) | bb_shift<0, 1>(r, c) |
+           bb_shift<-1, 1>(r, c) | bb_shift<-1, 0>(r, c);
+}
+
+__device__ __forceinline__ bool hex_connected(u64 stones, u64 start, u64 goal, const GameCfg& c) {
+    u64 reach = stones & start;
+    while (reach) {
+        if (reach & goal) return true;
+        u64 grow = hex_neighbours(reach, c) & stones & ~reach;
+        if (!grow) return false;
+        reach |= grow;
+    }
+    return false;
+}
+
+// ---------------------------------------------------------------------------- tictactoe
+__device__ __forceinline__ bool ttt_line(u64 b) {
+    return (b & 0007) == 0007 || (b & 0070) == 0070 || (b & 0700) == 0700 || (b & 0111) == 0111 ||
+           (b & 0222) == 0222 || (b & 0444) == 0444 || (b & 0421) == 0421 || (b & 0124) == 0124;
+}
+
+// ------------------------------------------------------------------------ generic logic
+__device__ __forceinline__ GState game_initial(const GameCfg& c) {
+    GState s;
+    s.player = 1;
+    s.first = s.second = 0;
+    if (c.game == DM_OTHELLO) {
+        int x = c.g / 2, y = c.g / 2;  // othello/game.py:43-47
+        s.second = (1ull << (y * c.g + x)) | (1ull << ((y - 1) * c.g + x - 1));
+        s.first = (1ull << (y * c.g + x - 1)) | (1ull << ((y - 1) * c.g + x));
+    }
+    return s;
+}
+
+// evaluate_final_state(...).value
+__device__ __forceinline__ float game_outcome(const GameCfg& c, const GState& s) {
+    if (c.game == DM_OTHELLO) {
+        int f = __popcll(s.first), sc = __popcll(s.second);  // othello/game.py:126-141
+        return f > sc ? 0.0f : (sc > f ? 1.0f : 0.5f);
+    }
+    if (c.game == DM_TICTACTOE) {
+        if (ttt_line(s.second)) return 1.0f;  // SECOND tested first, tictactoe/game.py:87-97
+        if (ttt_line(s.first)) return 0.0f;
+        return 0.5f;
+    }
+    if (hex_connected(s.second, c.col0, c.colL, c)) return 1.0f;  // hex/game.py:83-93
+    if (hex_connected(s.first, c.row0, c.rowL, c)) return 0.0f;   // hex/game.py:94-103
+    return 0.5f;
+}
+
+// legal cells as a mask plus whether the extra action (pass / swap) is legal
+__device__ __forceinline__ u64 game_legal_mask(const GameCfg& c, const GState& s, bool& extra) {
+    u64 occ = s.first | s.second;
+    extra = false;
+    if (c.game == DM_OTHELLO) {
+        u64 own = s.player ? s.first : s.second, opp = s.player ? s.second : s.first;
+        u64 m = othello_moves(own, opp, c);
+        extra = (m == 0);  // othello/game.py:116-117
+        return m;
+    }
+    if (c.game == DM_HEX_SWAP) extra = (s.player == 0) && (__popcll(occ) == 1);  // hex_with_swap/game.py:30-35
+    return ~occ & c.full;
+}
+
+__device__ __forceinline__ bool game_is_final(const GameCfg& c, const GState& s, float& outcome) {
+    outcome = game_outcome(c, s);
+    if (c.game == DM_OTHELLO) {
+        // othello/game.py:120-124: both sides can only pass
+        if (othello_moves(s.player ? s.first : s.second, s.player ? s.second : s.first, c)) return false;
+        return othello_moves(s.player ? s.second : s.first, s.player ? s.first : s.second, c) == 0;
+    }
+    if (c.game == DM_TICTACTOE) return outcome != 0.5f || ((s.first | s.second) == c.full);
+    return outcome != 0.5f;  // hex/game.py:74-76
+}
+
+__device__ __forceinline__ bool game_action_legal(const GameCfg& c, const GState& s, int action) {
+    bool extra;
+    u64 m = game_legal_mask(c, s, extra);
+    if (action < 0 || action >= c.num_actions) return false;
+    if (action == c.cells) return extra;
+    return (m >> action) & 1;
+}
+
+// generate_child_state for a legal action
+__device__ __forceinline__ GState game_child(const GameCfg& c, const GState& s, int action) {
+    GState r;
+    r.player = 1 - s.player;
+    if (action == c.cells) {
+        if (c.game == DM_HEX_SWAP) {  // recolour every stone, hex_with_swap/game.py:21-25
+            r.first = s.second;
+            r.second = s.first;
+        } else {  // othello pass, othello/game.py:55-56
+            r.first = s.first;
+            r.second = s.second;
+        }
+        return r;
+    }
+    u64 bit = 1ull << action;
+    u64 flips = 0;
+    if (c.game == DM_OTHELLO)
+        flips = othello_flips(s.player ? s.first : s.second, s.player ? s.second : s.first, bit, c);
+    if (s.player) {
+        r.first = s.first | bit | flips;
+        r.second = s.second & ~flips;
+    } else {
+        r.first = s.first & ~flips;
+        r.second = s.second | bit | flips;
+    }
+    return r;
+}
+
+// ---------------------------------------------------------------- CPython set ordering
+// A 32-slot open-addressing table held one slot per lane (8-slot phase uses lanes 0..7).
+// Only sets of <= 18 keys are emulated; >= 19 keys always iterate ascending (the table
+// has grown to 128 slots and every key < 128 sits in its own slot).
+struct WarpSet {
+    int slot;  // this lane's slot (-1 empty)
+    int size;  // 8 or 32
+    int fill;
+
+    __device__ __forceinline__ void init() {
+        slot = -1;
+        size = 8;
+        fill = 0;
+    }
+    __device__ __forceinline__ void place(int key, int lane) {
+        u32 mask = (u32)size - 1u;
+        u32 i = (u32)key & mask, perturb = (u32)key;
+        u32 empties = __ballot_sync(DM_FULL_MASK, slot < 0) & (size == 32 ? 0xffffffffu : 0xffu);
+        while (true) {
+            u32 window = ((i + 9u <= mask) ? 0x3ffu : 1u) << i;  // LINEAR_PROBES = 9
+            u32 hit = empties & window;
+            if (hit) {
+                if (lane == __ffs(hit) - 1) slot = key;
+                return;
+            }
+            perturb >>= 5;  // PERTURB_SHIFT
+            i = (i * 5u + 1u + perturb) & mask;
+        }
+    }
+    // key must not be in the set yet (callers dedup with a bitmask)
+    __device__ __forceinline__ void add(int key, int lane) {
+        place(key, lane);
+        ++fill;
+        if (size == 8 && fill * 5 >= 21) {  // fill*5 >= mask*3 -> grow to 32 (4*5 = 20 < 32)
+            int old = slot;
+            slot = -1;
+            size = 32;
+            for (int s = 0; s < 8; ++s) {
+                int k = __shfl_sync(DM_FULL_MASK, old, s);
+                if (k >= 0) place(k, lane);
+            }
+        }
+    }
+    // writes keys in slot order to out[0..fill)
+    __device__ __forceinline__ void emit(u8* out, int lane) const {
+        u32 used = __ballot_sync(DM_FULL_MASK, slot >= 0);
+        if (slot >= 0) out[__popc(used & ((1u << lane) - 1u))] = (u8)slot;
+    }
+};
+
+__device__ __forceinline__ void emit_ascending(u64 mask, bool extra, int extra_action, u8* out, int lane) {
+    // lane l writes the cells l and l+32 it owns
+    u32 lo = (u32)mask, hi = (u32)(mask >> 32);
+    if ((lo >> lane) & 1) out[__popc(lo & ((1u << lane) - 1u))] = (u8)lane;
+    if ((hi >> lane) & 1) out[__popc(lo) + __popc(hi & ((1u << lane) - 1u))] = (u8)(lane + 32);
+    if (extra && lane == 0) out[__popcll(mask)] = (u8)extra_action;
+}
+
+// Warp-cooperative.  Writes the order in which MCTS.expand_node creates children
+// (iteration order of set(legal_actions(state)), mcts.py:200-215) to order_out[0..n) and,
+// if list_out != nullptr, the reference's legal_actions LIST order to list_out[0..n).
+// Both buffers need DM_MAX_ACTIONS + 1 bytes visible to the whole warp.  Returns n.
+__device__ __forceinline__ int warp_children_order(const GameCfg& c, const GState& s, int lane, u8* order_out,
+                                                   u8* list_out) {
+    bool extra;
+    u64 mask = game_legal_mask(c, s, extra);
+    int n = __popcll(mask) + (extra ? 1 : 0);
+    if (c.game == DM_OTHELLO && mask == 0) {  // only pass
+        if (lane == 0) {
+            order_out[0] = (u8)c.cells;
+            if (list_out) list_out[0] = (u8)c.cells;
+        }
+        __syncwarp();
+        return 1;
+    }
+    if (c.game != DM_OTHELLO) {
+        // legal_actions is the ascending list (+ swap last); children = set(list)
+        if (list_out) emit_ascending(mask, extra, c.cells, list_out, lane);
+        if (n >= 19) {
+            emit_ascending(mask, extra, c.cells, order_out, lane);
+        } else {
+            WarpSet set;
+            set.init();
+            u64 m = mask;
+            while (m) {
+                int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                set.add(k, lane);
+            }
+            if (extra) set.add(c.cells, lane);
+            set.emit(order_out, lane);
+        }
+        __syncwarp();
+        return n;
+    }
+    // Othello: legal_actions itself returns list(set) built in discovery order
+    // (othello/game.py:88-118); expand_node wraps that list in a second set.
+    if (n >= 19) {
+        emit_ascending(mask, false, c.cells, order_out, lane);
+        if (list_out) emit_ascending(mask, false, c.cells, list_out, lane);
+        __syncwarp();
+        return n;
+    }
+    u64 own = s.player ? s.first : s.second, opp = s.player ? s.second : s.first;
+    WarpSet stage1;
+    stage1.init();
+    u64 seen = 0;
+    for (int half = 0; half < 2; ++half) {
+        int cell = lane + 32 * half;
+        u64 packed = ~0ull;  // 8 target bytes, 0xff = none
+        if (cell < c.cells && ((own >> cell) & 1)) {
+            u64 bit = 1ull << cell;
+            int d = 0;
+#define DM_DIR(DX, DY)                                                                                   \
+    {                                                                                                    \
+        u64 t = othello_ray_target<DX, DY>(own, opp, bit, c);                                            \
+        if (t) packed = (packed & ~(0xffull << (8 * d))) | ((u64)(__ffsll((long long)t) - 1) << (8 * d)); \
+        ++d;                                                                                             \
+    }
+            DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
+#undef DM_DIR
+        }
+        u32 active = __ballot_sync(DM_FULL_MASK, packed != ~0ull);
+        while (active) {
+            int src = __ffs(active) - 1;
+            active &= active - 1;
+            u64 p = __shfl_sync(DM_FULL_MASK, packed, src);
+#pragma unroll
+            for (int d = 0; d < 8; ++d) {
+                int k = (int)((p >> (8 * d)) & 0xff);
+                if (k != 0xff && !((seen >> k) & 1)) {
+                    seen |= 1ull << k;
+                    stage1.add(k, lane);
+                }
+            }
+        }
+    }
+    // second set: insert stage-1 keys in stage-1 slot order
+    WarpSet stage2;
+    stage2.init();
+    u32 used = __ballot_sync(DM_FULL_MASK, stage1.slot >= 0);
+    if (list_out) stage1.emit(list_out, lane);
+    while (used) {
+        int src = __ffs(used) - 1;
+        used &= used - 1;
+        stage2.add(__shfl_sync(DM_FULL_MASK, stage1.slot, src), lane);
+    }
+    stage2.emit(order_out, lane);
+    __syncwarp();
+    return n;
+}
+
+// ----------------------------------------------------------------------------- rollouts
+__device__ __forceinline__ int nth_set_bit(u64 m, int n) {
+    for (int i = 0; i < n; ++i) m &= m - 1;
+    return __ffsll((long long)m) - 1;
+}
+
+// MCTS.rollout (mcts.py:219-226) from a non-final state; returns the outcome value
+__device__ __forceinline__ float game_rollout(const GameCfg& c, GState s, int kind, Philox& rng, int& plies) {
+    float outcome;
+    plies = 0;
+    if (kind == DM_ROLLOUT_RANDOM && (c.game == DM_HEX || c.game == DM_HEX_SWAP)) {
+        // Uniform random alternate play until someone connects has the same winner
+        // distribution as filling the board alternately at random and reading the winner
+        // once: a completed Hex board has exactly one winner and the first winning chain
+        // survives further placements.
+        while (true) {
+            bool extra;
+            u64 m = game_legal_mask(c, s, extra);
+            int n = __popcll(m) + (extra ? 1 : 0);
+            if (n == 0) break;
+            int r = (int)rng.below((u32)n);
+            int a = (r == __popcll(m)) ? c.cells : nth_set_bit(m, r);
+            s = game_child(c, s, a);
+            ++plies;
+        }
+        return game_outcome(c, s);
+    }
+    while (!game_is_final(c, s, outcome)) {
+        bool extra;
+        u64 m = game_legal_mask(c, s, extra);
+        int cnt = __popcll(m);
+        int a;
+        if (cnt == 0) a = c.cells;  // othello pass is the only action
+        else if (kind == DM_ROLLOUT_RANDOM) {
+            int r = (int)rng.below((u32)(cnt + (extra ? 1 : 0)));
+            a = (r == cnt) ? c.cells : nth_set_bit(m, r);
+        } else if (kind == DM_ROLLOUT_MIN_ACTION) a = __ffsll((long long)m) - 1;
+        else a = extra ? c.cells : (63 - __clzll((long long)m));
+        s = game_child(c, s, a);
+        ++plies;
+    }
+    return outcome;
+}

@@ -1,0 +1,1167 @@
+// PUCT tree search over thousands of independent game trees, one warp per tree.
+//
+// Replaces MCTS.step / simulation / tree_search / evaluate_leaf / expand_node / rollout /
+// backpropagate / add_dirichlet_noise / self_play / reset and MCTSAgent.play's re-rooting
+// (reference deep_mcts/mcts.py:57-300) plus create_self_play_examples' labelling
+// (deep_mcts/train.py:258-283).
+//
+// Data layout (HBM, structure of arrays, tree t owns node slots [t*cap, (t+1)*cap)):
+//   visits u32 | value_sum f64 | prior f64 | first_child u32 | n_children u8 | action u8
+// The children of a node are contiguous and stored in the order the reference's dict
+// iterates them (CPython set order, games.cuh), so a warp scores up to 32 children per
+// coalesced load and first-extremum ties (mcts.py:167-176) resolve to the lowest child slot.
+// All PUCT arithmetic is IEEE double without contraction in the reference's operation
+// order, one simulation in flight per tree, which makes visit counts bit-identical to the
+// reference for the same evaluator outputs.
+#include "games.cuh"
+
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+constexpr u8 kFlagNeedNoise = 1;
+constexpr u8 kFlagStepActive = 2;
+constexpr u8 kLeafRoot = 1;  // leaf is a root expansion: only root.visits += 1 (mcts.py:114-116)
+
+enum Counter {
+    kCntSims = 0, kCntLeafEvals = 1, kCntTerminal = 2, kCntNodesHigh = 3, kCntGames = 4, kCntDepth = 5,
+    kCntScanned = 6, kCntCreated = 7, kCntCapacity = 8, kCntMoves = 9, kCntRolloutPlies = 10, kCntInvalid = 11
+};
+
+struct PoolView {
+    GameCfg cfg;
+    int n_trees;
+    u32 cap;
+    double c_puct;
+    u64 seed;
+    // search configuration (mcts.py:70-95)
+    int num_simulations, eval_kind, rollout_kind, sample_move_cutoff;
+    double dirichlet_alpha, dirichlet_factor, rollout_share;
+    u64 eval_salt;
+    const double* host_noise;  // [n_trees][DM_MAX_ACTIONS] in child order, or null
+    // nodes
+    u32* visits;
+    double* value_sum;
+    double* prior;
+    u32* first_child;
+    u8* n_children;
+    u8* action;
+    // per tree
+    u32* node_count;
+    u32* root;
+    u64* root_first;
+    u64* root_second;
+    u8* root_player;
+    int* sims_left;
+    u32* stat_with;
+    u32* stat_without;
+    u8* flags;
+    u32* ply;
+    u32* rng_ctr;
+    u32* path;      // [n_trees][DM_MAX_DEPTH] pending leaf's root-to-leaf path
+    int* path_len;  // [n_trees]
+    // pending leaf batch (compact)
+    u64* leaf_first;
+    u64* leaf_second;
+    u8* leaf_player;
+    u8* leaf_flags;
+    int* leaf_tree;
+    int* leaf_count;
+    unsigned long long* counters;
+    // self-play recording
+    int selfplay;
+    u64* ex_first;  // [n_trees][DM_MAX_DEPTH]
+    u64* ex_second;
+    u8* ex_player;
+    float* ex_pi;  // [n_trees][DM_MAX_DEPTH][DM_MAX_ACTIONS]
+    u64 replay_cap;
+    u64* rp_first;
+    u64* rp_second;
+    u8* rp_player;
+    float* rp_pi;
+    float* rp_z;
+    unsigned long long* rp_written;
+};
+
+// ------------------------------------------------------------------ small warp helpers
+__device__ __forceinline__ void count(const PoolView& P, int which, unsigned long long v) {
+    if (v) atomicAdd(&P.counters[which], v);
+}
+
+__device__ __forceinline__ GState root_state(const PoolView& P, int t) {
+    GState s;
+    s.first = P.root_first[t];
+    s.second = P.root_second[t];
+    s.player = P.root_player[t];
+    return s;
+}
+
+__device__ __forceinline__ void clear_node(const PoolView& P, size_t idx) {
+    P.visits[idx] = 0;
+    P.value_sum[idx] = 0.0;
+    P.prior[idx] = -1.0;
+    P.first_child[idx] = 0;
+    P.n_children[idx] = 0;
+    P.action[idx] = 0xff;
+}
+
+// fresh single-node tree on state s (lane 0 only)
+__device__ __forceinline__ void fresh_root(const PoolView& P, int t, const GState& s) {
+    size_t base = (size_t)t * P.cap;
+    clear_node(P, base);
+    P.node_count[t] = 1;
+    P.root[t] = 0;
+    P.root_first[t] = s.first;
+    P.root_second[t] = s.second;
+    P.root_player[t] = (u8)s.player;
+}
+
+// ---- synthetic integer-hash evaluator (oracle/evaluators.py: hashed_salted) -------------
+__device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 30;
+    x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27;
+    x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ u64 hashed_h0(const GState& s, u64 salt) {
+    return mix64(s.first ^ mix64(s.second ^ mix64((u64)s.player + 0x9E3779B97F4A7C15ull * (salt + 1))));
+}
+__device__ __forceinline__ u32 hashed_weight(u64 h0, int a) {
+    return (u32)((mix64(h0 + (u64)a * 0xD6E8FEB86659FD93ull) >> 40) % 997ull) + 1u;
+}
+
+// ------------------------------------------------------------------------------ select
+// tree_search (mcts.py:162-179): descend from the root while the node has children.
+// s_path (shared, per warp) receives the node indices; returns path length.
+__device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GState& s, u32* s_path,
+                                       unsigned long long& scanned, bool& overflow) {
+    const size_t base = (size_t)t * P.cap;
+    u32 node = P.root[t];
+    s = root_state(P, t);
+    int len = 0;
+    if (lane == 0) s_path[0] = node;
+    len = 1;
+    overflow = false;
+    while (true) {
+        int n = P.n_children[base + node];
+        if (n == 0) break;
+        u32 first = P.first_child[base + node];
+        double sq = sqrt((double)P.visits[base + node]);  // IEEE sqrt, as math.sqrt
+        bool maximise = (s.player == 0);                   // SECOND is the max player (game.py:31-33)
+        double unvisited = maximise ? 0.0 : 1.0;           // parent.player.loss().value (mcts.py:48-50)
+        double best_key = 0.0;
+        int best = -1;
+        for (int j = lane; j < n; j += 32) {
+            size_t c = base + first + j;
+            u32 v = P.visits[c];
+            double value = (v == 0) ? unvisited : __ddiv_rn(P.value_sum[c], (double)v);
+            // u = ((c_puct * P) * sqrt(N)) / (1 + n)   (mcts.py:40-43), no FMA contraction
+            double u = __ddiv_rn(__dmul_rn(__dmul_rn(P.c_puct, P.prior[c]), sq), (double)(1u + v));
+            double key = maximise ? __dadd_rn(value, u) : -__dsub_rn(value, u);
+            if (best < 0 || key > best_key) {
+                best_key = key;
+                best = j;
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double ok = __shfl_xor_sync(DM_FULL_MASK, best_key, off);
+            int ob = __shfl_xor_sync(DM_FULL_MASK, best, off);
+            if (ob >= 0 && (best < 0 || ok > best_key || (ok == best_key && ob < best))) {
+                best_key = ok;
+                best = ob;
+            }
+        }
+        scanned += (unsigned long long)n;
+        node = first + (u32)best;
+        s = game_child(P.cfg, s, P.action[base + node]);
+        if (len >= DM_MAX_DEPTH) {
+            overflow = true;
+            break;
+        }
+        if (lane == 0) s_path[len] = node;
+        ++len;
+    }
+    __syncwarp();
+    return len;
+}
+
+// backpropagate (mcts.py:228-231)
+__device__ __forceinline__ void backup(const PoolView& P, int t, int lane, const u32* path, int len, double value) {
+    const size_t base = (size_t)t * P.cap;
+    for (int i = lane; i < len; i += 32) {
+        size_t idx = base + path[i];
+        P.visits[idx] += 1;
+        P.value_sum[idx] = __dadd_rn(P.value_sum[idx], value);
+    }
+    __syncwarp();
+}
+
+// expand_node (mcts.py:198-217).  Priors come from the built-in evaluators or from an
+// external array (ext_f32 / ext_f64 indexed by action).  Returns false on capacity error.
+__device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 node, const GState& s, u8* s_order,
+                                       int eval_kind, const float* ext_f32, const double* ext_f64,
+                                       double& eval_value) {
+    const size_t base = (size_t)t * P.cap;
+    int n = warp_children_order(P.cfg, s, lane, s_order, nullptr);
+    u32 cnt = P.node_count[t];
+    if (cnt + (u32)n > P.cap) {
+        if (lane == 0) count(P, kCntCapacity, 1);
+        return false;
+    }
+    double uniform_p = __ddiv_rn(1.0, (double)n);
+    u64 h0 = 0;
+    double total = 1.0;
+    eval_value = 0.5;
+    if (eval_kind == DM_EVAL_HASHED) {
+        h0 = hashed_h0(s, P.eval_salt);
+        u32 sum = 0;
+        for (int j = lane; j < n; j += 32) sum += hashed_weight(h0, s_order[j]);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(DM_FULL_MASK, sum, off);
+        total = (double)sum;
+        eval_value = __ddiv_rn((double)((h0 >> 20) % 1001ull), 1000.0);
+    }
+    for (int j = lane; j < n; j += 32) {
+        size_t c = base + cnt + j;
+        int a = s_order[j];
+        double p;
+        if (eval_kind == DM_EVAL_HASHED) p = __ddiv_rn((double)hashed_weight(h0, a), total);
+        else if (eval_kind == DM_EVAL_EXTERNAL) p = ext_f64 ? ext_f64[a] : (double)ext_f32[a];
+        else p = uniform_p;
+        P.visits[c] = 0;
+        P.value_sum[c] = 0.0;
+        P.prior[c] = p;
+        P.first_child[c] = 0;
+        P.n_children[c] = 0;
+        P.action[c] = (u8)a;
+    }
+    if (lane == 0) {
+        P.first_child[base + node] = cnt;
+        P.n_children[base + node] = (u8)n;
+        P.node_count[t] = cnt + (u32)n;
+        count(P, kCntCreated, (unsigned long long)n);
+        atomicMax(&P.counters[kCntNodesHigh], (unsigned long long)(cnt + n));
+    }
+    __syncwarp();
+    return true;
+}
+
+// ---- Dirichlet noise (mcts.py:233-241) --------------------------------------------------
+__device__ __forceinline__ double sample_gamma(Philox& rng, double alpha) {
+    // Marsaglia-Tsang; alpha < 1 boosted through gamma(alpha + 1) * U^(1/alpha)
+    double boost = 1.0;
+    if (alpha < 1.0) {
+        boost = pow(rng.uniform(), 1.0 / alpha);
+        alpha += 1.0;
+    }
+    double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    while (true) {
+        double u1 = rng.uniform(), u2 = rng.uniform();
+        double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
+        double v = 1.0 + c * x;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        double u = rng.uniform();
+        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v * boost;
+    }
+}
+
+__device__ __forceinline__ void apply_root_noise(const PoolView& P, int t, int lane) {
+    const size_t base = (size_t)t * P.cap;
+    u32 root = P.root[t];
+    int n = P.n_children[base + root];
+    if (n == 0) return;
+    u32 first = P.first_child[base + root];
+    double noise[3] = {0.0, 0.0, 0.0};
+    if (P.host_noise) {
+        for (int k = 0, j = lane; j < n; j += 32, ++k) noise[k] = P.host_noise[(size_t)t * DM_MAX_ACTIONS + j];
+    } else {
+        Philox rng;
+        rng.init(P.seed, (u32)t, 0x6e6f6900u + (u32)lane, P.rng_ctr[t]);
+        double sum = 0.0;
+        for (int k = 0, j = lane; j < n; j += 32, ++k) {
+            noise[k] = sample_gamma(rng, P.dirichlet_alpha);
+            sum += noise[k];
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(DM_FULL_MASK, sum, off);
+        for (int k = 0; k < 3; ++k) noise[k] /= sum;
+        __syncwarp();
+        if (lane == 0) P.rng_ctr[t] += 64;
+    }
+    double keep = 1.0 - P.dirichlet_factor;
+    for (int k = 0, j = lane; j < n; j += 32, ++k) {
+        size_t c = base + first + j;
+        // probability * (1 - factor) + noise[i] * factor
+        P.prior[c] = __dadd_rn(__dmul_rn(P.prior[c], keep), __dmul_rn(noise[k], P.dirichlet_factor));
+    }
+    __syncwarp();
+}
+
+// arm one MCTS.step on tree t (lane 0)
+__device__ __forceinline__ void arm_step(const PoolView& P, int t) {
+    GState s = root_state(P, t);
+    float o;
+    bool final = game_is_final(P.cfg, s, o);
+    P.sims_left[t] = final ? 0 : P.num_simulations;
+    P.stat_with[t] = 0;
+    P.stat_without[t] = 0;
+    u8 f = P.flags[t] & ~(kFlagNeedNoise | kFlagStepActive);
+    if (!final) {
+        f |= kFlagStepActive;
+        if (P.dirichlet_alpha != 0.0) f |= kFlagNeedNoise;
+    }
+    P.flags[t] = f;
+}
+
+// leaf value for the local (no external evaluator) modes: evaluate_leaf, mcts.py:186-196
+__device__ __forceinline__ double mix_rollout(const PoolView& P, const GState& s, double eval_value, Philox& rng,
+                                              unsigned long long& plies) {
+    if (P.eval_kind == DM_EVAL_NONE) {
+        int p;
+        double r = (double)game_rollout(P.cfg, s, P.rollout_kind, rng, p);
+        plies += p;
+        return r;
+    }
+    if (P.rollout_kind == DM_ROLLOUT_NONE || (P.rollout_share < 1.0 && rng.uniform() >= P.rollout_share))
+        return eval_value;
+    int p;
+    double r = (double)game_rollout(P.cfg, s, P.rollout_kind, rng, p);
+    plies += p;
+    return __ddiv_rn(__dadd_rn(r, eval_value), 2.0);
+}
+
+// --------------------------------------------------------------------- kernels: admin
+__global__ void k_reset(PoolView P, const int* ids, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t = ids ? ids[i] : i;
+    if (t < 0 || t >= P.n_trees) return;
+    fresh_root(P, t, game_initial(P.cfg));
+    P.sims_left[t] = 0;
+    P.stat_with[t] = P.stat_without[t] = 0;
+    P.flags[t] = 0;
+    P.ply[t] = 0;
+    P.path_len[t] = 0;
+}
+
+__global__ void k_set_root(PoolView P, const int* ids, int n, const u64* first, const u64* second,
+                           const u8* player) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t = ids ? ids[i] : i;
+    if (t < 0 || t >= P.n_trees) return;
+    GState s;
+    s.first = first[i];
+    s.second = second[i];
+    s.player = player[i];
+    fresh_root(P, t, s);
+    P.sims_left[t] = 0;
+    P.flags[t] = 0;
+}
+
+// MCTSAgent.play (mcts.py:267-283): first child (dict order) whose state equals the observed one
+__global__ void k_observe(PoolView P, const int* ids, int n, const u64* first, const u64* second,
+                          const u8* player) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int i = blockIdx.x * kWarpsPerBlock + warp;
+    if (i >= n) return;
+    int t = ids ? ids[i] : i;
+    if (t < 0 || t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    GState want;
+    want.first = first[i];
+    want.second = second[i];
+    want.player = player[i];
+    GState cur = root_state(P, t);
+    u32 root = P.root[t];
+    int nc = P.n_children[base + root];
+    u32 fc = P.first_child[base + root];
+    int found = -1;
+    for (int j0 = 0; j0 < nc && found < 0; j0 += 32) {
+        int j = j0 + lane;
+        bool match = false;
+        if (j < nc) {
+            GState c = game_child(P.cfg, cur, P.action[base + fc + j]);
+            match = (c.first == want.first && c.second == want.second && c.player == want.player);
+        }
+        u32 m = __ballot_sync(DM_FULL_MASK, match);
+        if (m) found = j0 + __ffs(m) - 1;
+    }
+    if (lane == 0) {
+        if (found >= 0) {
+            P.root[t] = fc + (u32)found;
+            P.root_first[t] = want.first;
+            P.root_second[t] = want.second;
+            P.root_player[t] = (u8)want.player;
+        } else {
+            fresh_root(P, t, want);
+        }
+        P.sims_left[t] = 0;
+    }
+}
+
+__global__ void k_begin_step(PoolView P) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_trees) return;
+    arm_step(P, t);
+}
+
+// ------------------------------------------------------- kernel: whole search in one launch
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search_local(PoolView P) {
+    __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
+    __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    int sims = P.sims_left[t];
+    if (sims <= 0) return;
+    const size_t base = (size_t)t * P.cap;
+    u32* path = s_path[warp];
+    u8* order = s_order[warp];
+    Philox rng;
+    rng.init(P.seed, (u32)t, 0x73696d00u, P.rng_ctr[t]);
+    unsigned long long scanned = 0, depth = 0, plies = 0, evals = 0, terminal = 0, done = 0;
+    bool dead = false;
+    double ev;
+    u32 root = P.root[t];
+    if (P.n_children[base + root] == 0) {
+        // step(): expand the root, root.visits += 1 (mcts.py:114-116)
+        GState s = root_state(P, t);
+        if (expand(P, t, lane, root, s, order, P.eval_kind, nullptr, nullptr, ev)) {
+            if (lane == 0) P.visits[base + root] += 1;
+            if (P.eval_kind != DM_EVAL_NONE) ++evals;
+        } else {
+            dead = true;
+        }
+        __syncwarp();
+    }
+    u8 flags = P.flags[t];
+    if (!dead && (flags & kFlagNeedNoise)) {
+        apply_root_noise(P, t, lane);
+        flags &= ~kFlagNeedNoise;
+    }
+    u32 with = P.stat_with[t], without = P.stat_without[t];
+    while (!dead && sims > 0) {
+        GState s;
+        bool overflow;
+        int len = descend(P, t, lane, s, path, scanned, overflow);
+        if (overflow) {
+            if (lane == 0) count(P, kCntCapacity, 1);
+            break;
+        }
+        depth += (unsigned long long)(len - 1);
+        float outcome;
+        double value;
+        if (game_is_final(P.cfg, s, outcome)) {
+            value = (double)outcome;  // mcts.py:182-185
+            ++without;
+            ++terminal;
+        } else {
+            if (!expand(P, t, lane, path[len - 1], s, order, P.eval_kind, nullptr, nullptr, ev)) break;
+            if (P.eval_kind != DM_EVAL_NONE) ++evals;
+            value = mix_rollout(P, s, ev, rng, plies);
+            ++with;
+        }
+        backup(P, t, lane, path, len, value);
+        --sims;
+        ++done;
+    }
+    if (lane == 0) {
+        P.sims_left[t] = dead ? 0 : sims;
+        P.stat_with[t] = with;
+        P.stat_without[t] = without;
+        P.flags[t] = flags;
+        P.rng_ctr[t] = rng.c0 + 1;
+        count(P, kCntSims, done);
+        count(P, kCntLeafEvals, evals);
+        count(P, kCntTerminal, terminal);
+        count(P, kCntDepth, depth);
+        count(P, kCntScanned, scanned);
+        count(P, kCntRolloutPlies, plies);
+    }
+}
+
+// -------------------------------------------------- self-play move / game bookkeeping
+// MCTS.self_play's move choice and re-rooting (mcts.py:96-111) and the example labelling
+// of create_self_play_examples (train.py:267-283).  Whole warp.
+__device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) {
+    const size_t base = (size_t)t * P.cap;
+    u32 root = P.root[t];
+    int n = P.n_children[base + root];
+    u32 first = P.first_child[base + root];
+    GState s = root_state(P, t);
+    u32 ply = P.ply[t];
+    // visit totals
+    u32 v[3] = {0, 0, 0};
+    int a[3] = {0, 0, 0};
+    u32 total = 0;
+    for (int k = 0, j = lane; j < n; j += 32, ++k) {
+        v[k] = P.visits[base + first + j];
+        a[k] = P.action[base + first + j];
+        total += v[k];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) total += __shfl_xor_sync(DM_FULL_MASK, total, off);
+    // record (state, pi) (train.py:267-268)
+    bool record = ply < DM_MAX_DEPTH;
+    if (record) {
+        size_t e = (size_t)t * DM_MAX_DEPTH + ply;
+        float* pi = P.ex_pi + e * DM_MAX_ACTIONS;
+        for (int j = lane; j < DM_MAX_ACTIONS; j += 32) pi[j] = 0.0f;
+        __syncwarp();
+        for (int k = 0, j = lane; j < n; j += 32, ++k)
+            pi[a[k]] = total ? (float)((double)v[k] / (double)total) : 1.0f / (float)n;
+        if (lane == 0) {
+            P.ex_first[e] = s.first;
+            P.ex_second[e] = s.second;
+            P.ex_player[e] = (u8)s.player;
+        }
+    }
+    // choose the move
+    int chosen = -1;
+    if ((int)ply < P.sample_move_cutoff && total > 0) {
+        // np.random.choice(len(pi), p=pi): proportional to visit counts
+        Philox rng;
+        rng.init(P.seed, (u32)t, 0x6d6f7665u, P.rng_ctr[t]);
+        u32 r = rng.below(total);
+        // order children by action id so the draw is a function of (r, visits by action)
+        chosen = -1;
+        u32 acc_best = 0xffffffffu;
+        for (int k = 0, j = lane; j < n; j += 32, ++k) {
+            // cumulative visits of all children with action id <= a[k]
+            u32 cum = 0;
+            for (int jj = 0; jj < n; ++jj)
+                if (P.action[base + first + jj] <= a[k]) cum += P.visits[base + first + jj];
+            if (v[k] > 0 && cum > r && cum < acc_best) {
+                acc_best = cum;
+                chosen = a[k];
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            u32 ob = __shfl_xor_sync(DM_FULL_MASK, acc_best, off);
+            int oc = __shfl_xor_sync(DM_FULL_MASK, chosen, off);
+            if (ob < acc_best) {
+                acc_best = ob;
+                chosen = oc;
+            }
+        }
+        if (lane == 0) P.rng_ctr[t] += 1;
+    }
+    if (chosen < 0) {
+        // np.argmax(pi): most visits, lowest action id on ties
+        u32 bv = 0;
+        int ba = 0x7fffffff;
+        for (int k = 0, j = lane; j < n; j += 32, ++k)
+            if (v[k] > bv || (v[k] == bv && a[k] < ba)) {
+                bv = v[k];
+                ba = a[k];
+            }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            u32 ov = __shfl_xor_sync(DM_FULL_MASK, bv, off);
+            int oa = __shfl_xor_sync(DM_FULL_MASK, ba, off);
+            if (ov > bv || (ov == bv && oa < ba)) {
+                bv = ov;
+                ba = oa;
+            }
+        }
+        chosen = ba;
+    }
+    // re-root with subtree reuse
+    int child = -1;
+    for (int k = 0, j = lane; j < n; j += 32, ++k)
+        if (a[k] == chosen) child = j;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) child = max(child, __shfl_xor_sync(DM_FULL_MASK, child, off));
+    GState ns = game_child(P.cfg, s, chosen);
+    ++ply;
+    float outcome;
+    bool final = game_is_final(P.cfg, ns, outcome);
+    if (final) {
+        // label every recorded position with the outcome from its mover's perspective
+        u32 cnt = min(ply, (u32)DM_MAX_DEPTH);
+        unsigned long long slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(P.rp_written, (unsigned long long)cnt);
+        slot0 = __shfl_sync(DM_FULL_MASK, slot0, 0);
+        float z = outcome * 2.0f - 1.0f;  // train.py:270-272
+        for (u32 i = 0; i < cnt; ++i) {
+            size_t e = (size_t)t * DM_MAX_DEPTH + i;
+            size_t r = (size_t)((slot0 + i) % P.replay_cap);
+            for (int j = lane; j < DM_MAX_ACTIONS; j += 32)
+                P.rp_pi[r * DM_MAX_ACTIONS + j] = P.ex_pi[e * DM_MAX_ACTIONS + j];
+            if (lane == 0) {
+                u8 pl = P.ex_player[e];
+                P.rp_first[r] = P.ex_first[e];
+                P.rp_second[r] = P.ex_second[e];
+                P.rp_player[r] = pl;
+                P.rp_z[r] = (pl == 0) ? z : -z;  // train.py:278-280
+            }
+        }
+        if (lane == 0) {
+            fresh_root(P, t, game_initial(P.cfg));
+            P.ply[t] = 0;
+            count(P, kCntGames, 1);
+        }
+    } else if (lane == 0) {
+        P.root[t] = first + (u32)child;
+        P.root_first[t] = ns.first;
+        P.root_second[t] = ns.second;
+        P.root_player[t] = (u8)ns.player;
+        P.ply[t] = ply;
+    }
+    if (lane == 0) count(P, kCntMoves, 1);
+    __syncwarp();
+    if (lane == 0) arm_step(P, t);
+    __syncwarp();
+}
+
+// --------------------------------------------------- kernel: external-evaluator select
+template <bool kSelfPlay>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select(PoolView P) {
+    __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    u32* path = s_path[warp];
+    unsigned long long scanned = 0, depth = 0, terminal = 0, done = 0;
+    if (kSelfPlay) {
+        if (P.sims_left[t] <= 0) {
+            if (P.flags[t] & kFlagStepActive) finish_move(P, t, lane);
+            else {
+                if (lane == 0) arm_step(P, t);
+                __syncwarp();
+            }
+        }
+    }
+    int sims = P.sims_left[t];
+    u8 flags = P.flags[t];
+    u32 without = P.stat_without[t];
+    bool emitted = false;
+    while (sims > 0) {
+        u32 root = P.root[t];
+        GState s;
+        int len;
+        u8 leaf_flag = 0;
+        if (P.n_children[base + root] == 0) {
+            // the root itself must be expanded first (mcts.py:114-116)
+            s = root_state(P, t);
+            if (lane == 0) path[0] = root;
+            len = 1;
+            leaf_flag = kLeafRoot;
+            __syncwarp();
+        } else {
+            if (flags & kFlagNeedNoise) {
+                apply_root_noise(P, t, lane);
+                flags &= ~kFlagNeedNoise;
+            }
+            bool overflow;
+            len = descend(P, t, lane, s, path, scanned, overflow);
+            if (overflow) {
+                if (lane == 0) count(P, kCntCapacity, 1);
+                sims = 0;
+                break;
+            }
+            depth += (unsigned long long)(len - 1);
+            float outcome;
+            if (game_is_final(P.cfg, s, outcome)) {
+                backup(P, t, lane, path, len, (double)outcome);
+                ++without;
+                ++terminal;
+                ++done;
+                --sims;
+                continue;
+            }
+        }
+        // hand the leaf to the evaluator
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(P.leaf_count, 1);
+        slot = __shfl_sync(DM_FULL_MASK, slot, 0);
+        for (int i = lane; i < len; i += 32) P.path[(size_t)t * DM_MAX_DEPTH + i] = path[i];
+        if (lane == 0) {
+            P.path_len[t] = len;
+            P.leaf_first[slot] = s.first;
+            P.leaf_second[slot] = s.second;
+            P.leaf_player[slot] = (u8)s.player;
+            P.leaf_flags[slot] = leaf_flag;
+            P.leaf_tree[slot] = t;
+        }
+        emitted = true;
+        break;
+    }
+    if (lane == 0) {
+        P.sims_left[t] = sims;
+        P.stat_without[t] = without;
+        P.flags[t] = flags;
+        if (!emitted) P.path_len[t] = 0;
+        count(P, kCntSims, done);
+        count(P, kCntTerminal, terminal);
+        count(P, kCntDepth, depth);
+        count(P, kCntScanned, scanned);
+    }
+}
+
+// expand_node + rollout mix + backpropagate for the leaves handed out by k_select
+template <typename PriorT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_expand_backup(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
+    __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int slot = blockIdx.x * kWarpsPerBlock + warp;
+    if (slot >= *P.leaf_count) return;
+    int t = P.leaf_tree[slot];
+    const size_t base = (size_t)t * P.cap;
+    int len = P.path_len[t];
+    if (len <= 0) return;
+    const u32* path = P.path + (size_t)t * DM_MAX_DEPTH;
+    GState s;
+    s.first = P.leaf_first[slot];
+    s.second = P.leaf_second[slot];
+    s.player = P.leaf_player[slot];
+    u8 leaf_flag = P.leaf_flags[slot];
+    double ev;
+    const PriorT* pr = priors + (size_t)slot * stride;
+    bool ok;
+    if (sizeof(PriorT) == 8) ok = expand(P, t, lane, path[len - 1], s, s_order[warp], DM_EVAL_EXTERNAL, nullptr,
+                                         (const double*)pr, ev);
+    else ok = expand(P, t, lane, path[len - 1], s, s_order[warp], DM_EVAL_EXTERNAL, (const float*)pr, nullptr, ev);
+    if (!ok) {
+        if (lane == 0) {
+            P.sims_left[t] = 0;
+            P.path_len[t] = 0;
+        }
+        return;
+    }
+    unsigned long long plies = 0;
+    if (leaf_flag & kLeafRoot) {
+        if (lane == 0) P.visits[base + path[0]] += 1;  // root.visits += 1, value unused
+        __syncwarp();
+        u8 flags = P.flags[t];
+        if (flags & kFlagNeedNoise) {
+            apply_root_noise(P, t, lane);
+            if (lane == 0) P.flags[t] = flags & ~kFlagNeedNoise;
+        }
+    } else {
+        double value = (double)values[slot];
+        if (P.rollout_kind != DM_ROLLOUT_NONE) {
+            Philox rng;
+            rng.init(P.seed, (u32)t, 0x73696d00u, P.rng_ctr[t]);
+            value = mix_rollout(P, s, value, rng, plies);
+            if (lane == 0) P.rng_ctr[t] = rng.c0 + 1;
+        }
+        backup(P, t, lane, path, len, value);
+        if (lane == 0) {
+            P.sims_left[t] -= 1;
+            P.stat_with[t] += 1;
+            count(P, kCntSims, 1);
+        }
+    }
+    if (lane == 0) {
+        P.path_len[t] = 0;
+        count(P, kCntLeafEvals, 1);
+        count(P, kCntRolloutPlies, plies);
+    }
+}
+
+// ------------------------------------------------------------------- kernels: read-out
+__global__ void k_root_visits(PoolView P, u32* visits_out, u32* stats_out) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    u32 root = P.root[t];
+    int n = P.n_children[base + root];
+    u32 first = P.first_child[base + root];
+    if (visits_out) {
+        for (int j = lane; j < DM_MAX_ACTIONS; j += 32) visits_out[(size_t)t * DM_MAX_ACTIONS + j] = 0;
+        __syncwarp();
+        for (int j = lane; j < n; j += 32)
+            visits_out[(size_t)t * DM_MAX_ACTIONS + P.action[base + first + j]] = P.visits[base + first + j];
+    }
+    if (stats_out && lane == 0) {
+        stats_out[2 * t] = P.stat_with[t];
+        stats_out[2 * t + 1] = P.stat_without[t];
+    }
+}
+
+__global__ void k_root_children(PoolView P, u8* order_out, int* count_out, u32* root_visits_out) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    u32 root = P.root[t];
+    int n = P.n_children[base + root];
+    u32 first = P.first_child[base + root];
+    if (order_out)
+        for (int j = lane; j < DM_MAX_ACTIONS; j += 32)
+            order_out[(size_t)t * DM_MAX_ACTIONS + j] = j < n ? P.action[base + first + j] : 0xff;
+    if (lane == 0) {
+        if (count_out) count_out[t] = n;
+        if (root_visits_out) root_visits_out[t] = P.visits[base + root];
+    }
+}
+
+__global__ void k_advance(PoolView P, const int* actions) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    int a = actions[t];
+    if (a < 0) return;
+    const size_t base = (size_t)t * P.cap;
+    u32 root = P.root[t];
+    int n = P.n_children[base + root];
+    u32 first = P.first_child[base + root];
+    int child = -1;
+    for (int j = lane; j < n; j += 32)
+        if (P.action[base + first + j] == a) child = j;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) child = max(child, __shfl_xor_sync(DM_FULL_MASK, child, off));
+    if (lane != 0) return;
+    GState s = root_state(P, t);
+    if (child < 0) {
+        // root not expanded (or action illegal): follow the reference's Node() fallback
+        // only when the action is legal; otherwise flag it
+        if (!game_action_legal(P.cfg, s, a)) {
+            count(P, kCntInvalid, 1);
+            return;
+        }
+        fresh_root(P, t, game_child(P.cfg, s, a));
+    } else {
+        GState ns = game_child(P.cfg, s, a);
+        P.root[t] = first + (u32)child;
+        P.root_first[t] = ns.first;
+        P.root_second[t] = ns.second;
+        P.root_player[t] = (u8)ns.player;
+    }
+    P.ply[t] += 1;
+    P.sims_left[t] = 0;
+    P.flags[t] &= ~(kFlagNeedNoise | kFlagStepActive);
+}
+
+__global__ void k_states(PoolView P, u64* first, u64* second, u8* player, u8* is_final, float* outcome) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= P.n_trees) return;
+    GState s = root_state(P, t);
+    if (first) first[t] = s.first;
+    if (second) second[t] = s.second;
+    if (player) player[t] = (u8)s.player;
+    if (is_final || outcome) {
+        float o;
+        bool f = game_is_final(P.cfg, s, o);
+        if (is_final) is_final[t] = f ? 1 : 0;
+        if (outcome) outcome[t] = o;
+    }
+}
+
+}  // namespace
+
+// =========================================================================== host side
+struct dm_pool {
+    PoolView v;
+    dm_pool_config cfg;
+    std::vector<void*> allocations;
+    bool configured;
+};
+
+namespace {
+
+template <typename T>
+int pool_alloc(dm_pool* p, T** out, size_t count, bool zero = true) {
+    void* ptr = nullptr;
+    DM_CUDA(cudaMalloc(&ptr, count * sizeof(T)));
+    p->allocations.push_back(ptr);
+    if (zero) DM_CUDA(cudaMemset(ptr, 0, count * sizeof(T)));
+    *out = (T*)ptr;
+    return DM_OK;
+}
+
+inline int tree_blocks(int n) { return (n + kWarpsPerBlock - 1) / kWarpsPerBlock; }
+
+}  // namespace
+
+#define DM_TRY(expr)                 \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ != DM_OK) return rc__; \
+    } while (0)
+
+extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
+    DM_CHECK_ARG(cfg && out, "dm_pool_create: null argument");
+    DM_CHECK_ARG(game_cfg_valid(cfg->game, cfg->grid), "dm_pool_create: unsupported game/grid");
+    DM_CHECK_ARG(cfg->n_trees > 0 && cfg->max_nodes_per_tree >= 2, "dm_pool_create: bad sizes");
+    DM_CUDA(cudaSetDevice(cfg->device));
+    dm_pool* p = new (std::nothrow) dm_pool();
+    DM_CHECK_ARG(p, "dm_pool_create: out of host memory");
+    p->cfg = *cfg;
+    p->configured = false;
+    PoolView& v = p->v;
+    memset(&v, 0, sizeof(v));
+    v.cfg = make_game_cfg(cfg->game, cfg->grid);
+    v.n_trees = cfg->n_trees;
+    v.cap = (u32)cfg->max_nodes_per_tree;
+    v.c_puct = cfg->c_puct;
+    v.seed = cfg->seed;
+    v.num_simulations = 0;
+    v.eval_kind = DM_EVAL_EXTERNAL;
+    v.rollout_kind = DM_ROLLOUT_NONE;
+    v.dirichlet_factor = 0.25;
+    v.rollout_share = 1.0;
+    size_t T = (size_t)cfg->n_trees, N = T * (size_t)v.cap;
+    int rc = DM_OK;
+    auto fail = [&](int code) {
+        dm_pool_destroy(p);
+        return code;
+    };
+    // node arrays are not zeroed: fresh_root / expand initialise every slot they publish
+    if ((rc = pool_alloc(p, &v.visits, N, false)) || (rc = pool_alloc(p, &v.value_sum, N, false)) ||
+        (rc = pool_alloc(p, &v.prior, N, false)) || (rc = pool_alloc(p, &v.first_child, N, false)) ||
+        (rc = pool_alloc(p, &v.n_children, N, false)) || (rc = pool_alloc(p, &v.action, N, false)) ||
+        (rc = pool_alloc(p, &v.node_count, T)) || (rc = pool_alloc(p, &v.root, T)) ||
+        (rc = pool_alloc(p, &v.root_first, T)) || (rc = pool_alloc(p, &v.root_second, T)) ||
+        (rc = pool_alloc(p, &v.root_player, T)) || (rc = pool_alloc(p, &v.sims_left, T)) ||
+        (rc = pool_alloc(p, &v.stat_with, T)) || (rc = pool_alloc(p, &v.stat_without, T)) ||
+        (rc = pool_alloc(p, &v.flags, T)) || (rc = pool_alloc(p, &v.ply, T)) ||
+        (rc = pool_alloc(p, &v.rng_ctr, T)) || (rc = pool_alloc(p, &v.path, T * DM_MAX_DEPTH)) ||
+        (rc = pool_alloc(p, &v.path_len, T)) || (rc = pool_alloc(p, &v.leaf_first, T)) ||
+        (rc = pool_alloc(p, &v.leaf_second, T)) || (rc = pool_alloc(p, &v.leaf_player, T)) ||
+        (rc = pool_alloc(p, &v.leaf_flags, T)) || (rc = pool_alloc(p, &v.leaf_tree, T)) ||
+        (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)))
+        return fail(rc);
+    k_reset<<<(cfg->n_trees + 127) / 128, 128>>>(v, nullptr, cfg->n_trees);
+    ++g_dm_launches;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        dm_set_error(std::string("dm_pool_create: ") + cudaGetErrorString(e));
+        return fail(DM_ERR_CUDA);
+    }
+    *out = p;
+    return DM_OK;
+}
+
+extern "C" int dm_pool_destroy(dm_pool* p) {
+    if (!p) return DM_OK;
+    cudaSetDevice(p->cfg.device);
+    for (void* ptr : p->allocations) cudaFree(ptr);
+    delete p;
+    return DM_OK;
+}
+
+extern "C" int dm_pool_configure(dm_pool* p, const dm_search_config* sc) {
+    DM_CHECK_ARG(p && sc, "dm_pool_configure: null argument");
+    DM_CHECK_ARG(sc->num_simulations >= 0, "dm_pool_configure: num_simulations < 0");
+    DM_CHECK_ARG(sc->eval_kind >= DM_EVAL_NONE && sc->eval_kind <= DM_EVAL_EXTERNAL, "dm_pool_configure: eval_kind");
+    DM_CHECK_ARG(sc->rollout_kind >= DM_ROLLOUT_NONE && sc->rollout_kind <= DM_ROLLOUT_MAX_ACTION,
+                 "dm_pool_configure: rollout_kind");
+    // mcts.py:82-83
+    DM_CHECK_ARG(!(sc->eval_kind == DM_EVAL_NONE && sc->rollout_kind == DM_ROLLOUT_NONE),
+                 "Both rollout_policy and state_evaluator cannot be None");
+    PoolView& v = p->v;
+    v.num_simulations = sc->num_simulations;
+    v.eval_kind = sc->eval_kind;
+    v.rollout_kind = sc->rollout_kind;
+    v.sample_move_cutoff = sc->sample_move_cutoff;
+    v.dirichlet_alpha = sc->dirichlet_alpha;
+    v.dirichlet_factor = sc->dirichlet_factor;
+    v.rollout_share = sc->rollout_share;
+    v.eval_salt = sc->eval_salt;
+    p->configured = true;
+    return DM_OK;
+}
+
+extern "C" int dm_pool_reset(dm_pool* p, const int32_t* ids, int n, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_reset: null pool");
+    if (!ids) n = p->v.n_trees;
+    DM_CHECK_ARG(n >= 0, "dm_pool_reset: n < 0");
+    if (n == 0) return DM_OK;
+    k_reset<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v, ids, n);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_set_root_state(dm_pool* p, const int32_t* ids, int n, const uint64_t* first,
+                                      const uint64_t* second, const uint8_t* player, void* stream) {
+    DM_CHECK_ARG(p && first && second && player, "dm_pool_set_root_state: null argument");
+    if (!ids) n = p->v.n_trees;
+    if (n <= 0) return DM_OK;
+    k_set_root<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v, ids, n, (const u64*)first,
+                                                                  (const u64*)second, player);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_observe(dm_pool* p, const int32_t* ids, int n, const uint64_t* first,
+                               const uint64_t* second, const uint8_t* player, void* stream) {
+    DM_CHECK_ARG(p && first && second && player, "dm_pool_observe: null argument");
+    if (!ids) n = p->v.n_trees;
+    if (n <= 0) return DM_OK;
+    k_observe<<<tree_blocks(n), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v, ids, n, (const u64*)first,
+                                                                                (const u64*)second, player);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_begin_step(dm_pool* p, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_begin_step: null pool");
+    if (!p->configured) {
+        dm_set_error("dm_pool_begin_step: dm_pool_configure has not been called");
+        return DM_ERR_STATE;
+    }
+    k_begin_step<<<(p->v.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_set_noise(dm_pool* p, const double* noise_dev) {
+    DM_CHECK_ARG(p, "dm_pool_set_noise: null pool");
+    p->v.host_noise = noise_dev;
+    return DM_OK;
+}
+
+extern "C" int dm_pool_search_local(dm_pool* p, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_search_local: null pool");
+    if (!p->configured || p->v.eval_kind == DM_EVAL_EXTERNAL) {
+        dm_set_error("dm_pool_search_local: needs eval_kind NONE / UNIFORM / HASHED");
+        return DM_ERR_STATE;
+    }
+    k_search_local<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+static int launch_select(dm_pool* p, void* stream, bool selfplay) {
+    if (!p->configured || p->v.eval_kind != DM_EVAL_EXTERNAL) {
+        dm_set_error("dm_pool_select: needs eval_kind EXTERNAL");
+        return DM_ERR_STATE;
+    }
+    DM_CUDA(cudaMemsetAsync(p->v.leaf_count, 0, sizeof(int), (cudaStream_t)stream));
+    if (selfplay)
+        k_select<true><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v);
+    else
+        k_select<false><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_select(dm_pool* p, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_select: null pool");
+    return launch_select(p, stream, false);
+}
+
+extern "C" int dm_pool_leaf_buffers(dm_pool* p, uint64_t** first, uint64_t** second, uint8_t** player,
+                                    int32_t** tree, int32_t** count) {
+    DM_CHECK_ARG(p, "dm_pool_leaf_buffers: null pool");
+    if (first) *first = (uint64_t*)p->v.leaf_first;
+    if (second) *second = (uint64_t*)p->v.leaf_second;
+    if (player) *player = p->v.leaf_player;
+    if (tree) *tree = p->v.leaf_tree;
+    if (count) *count = p->v.leaf_count;
+    return DM_OK;
+}
+
+extern "C" int dm_pool_expand_backup(dm_pool* p, const void* priors, int stride, const void* values, int is_f64,
+                                     void* stream) {
+    DM_CHECK_ARG(p && priors && values, "dm_pool_expand_backup: null argument");
+    DM_CHECK_ARG(stride >= p->v.cfg.num_actions, "dm_pool_expand_backup: prior_stride < num_actions");
+    if (is_f64)
+        k_expand_backup<double><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            p->v, (const double*)priors, stride, (const double*)values);
+    else
+        k_expand_backup<float><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+            p->v, (const float*)priors, stride, (const float*)values);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_root_visits(dm_pool* p, uint32_t* visits, uint32_t* stats, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_root_visits: null pool");
+    k_root_visits<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v, visits, stats);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_root_children(dm_pool* p, uint8_t* order, int32_t* count_out, uint32_t* root_visits,
+                                     void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_root_children: null pool");
+    k_root_children<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v, order, count_out,
+                                                                                                 root_visits);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_advance(dm_pool* p, const int32_t* actions, void* stream) {
+    DM_CHECK_ARG(p && actions, "dm_pool_advance: null argument");
+    k_advance<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v, actions);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_states(dm_pool* p, uint64_t* first, uint64_t* second, uint8_t* player, uint8_t* is_final,
+                              float* outcome, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_states: null pool");
+    k_states<<<(p->v.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v, (u64*)first, (u64*)second, player,
+                                                                         is_final, outcome);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_counters(dm_pool* p, uint64_t out[16]) {
+    DM_CHECK_ARG(p && out, "dm_pool_counters: null argument");
+    DM_CUDA(cudaSetDevice(p->cfg.device));
+    DM_CUDA(cudaDeviceSynchronize());
+    DM_CUDA(cudaMemcpy(out, p->v.counters, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (out[kCntCapacity]) {
+        dm_set_error("a tree ran out of node or path capacity (raise max_nodes_per_tree)");
+        return DM_ERR_CAPACITY;
+    }
+    return DM_OK;
+}
+
+extern "C" int dm_selfplay_enable(dm_pool* p, int replay_capacity) {
+    DM_CHECK_ARG(p && replay_capacity > 0, "dm_selfplay_enable: bad arguments");
+    if (p->v.selfplay) return DM_OK;
+    DM_CUDA(cudaSetDevice(p->cfg.device));
+    PoolView& v = p->v;
+    size_t T = (size_t)v.n_trees, E = T * DM_MAX_DEPTH, R = (size_t)replay_capacity;
+    DM_TRY(pool_alloc(p, &v.ex_first, E));
+    DM_TRY(pool_alloc(p, &v.ex_second, E));
+    DM_TRY(pool_alloc(p, &v.ex_player, E));
+    DM_TRY(pool_alloc(p, &v.ex_pi, E * DM_MAX_ACTIONS, false));
+    DM_TRY(pool_alloc(p, &v.rp_first, R));
+    DM_TRY(pool_alloc(p, &v.rp_second, R));
+    DM_TRY(pool_alloc(p, &v.rp_player, R));
+    DM_TRY(pool_alloc(p, &v.rp_pi, R * DM_MAX_ACTIONS));
+    DM_TRY(pool_alloc(p, &v.rp_z, R));
+    DM_TRY(pool_alloc(p, &v.rp_written, 1));
+    v.replay_cap = R;
+    v.selfplay = 1;
+    return DM_OK;
+}
+
+extern "C" int dm_selfplay_select(dm_pool* p, void* stream) {
+    DM_CHECK_ARG(p, "dm_selfplay_select: null pool");
+    if (!p->v.selfplay) {
+        dm_set_error("dm_selfplay_select: call dm_selfplay_enable first");
+        return DM_ERR_STATE;
+    }
+    return launch_select(p, stream, true);
+}
+
+extern "C" int dm_selfplay_replay(dm_pool* p, uint64_t** first, uint64_t** second, uint8_t** player, float** pi,
+                                  float** z, uint64_t** written) {
+    DM_CHECK_ARG(p && p->v.selfplay, "dm_selfplay_replay: self-play not enabled");
+    if (first) *first = (uint64_t*)p->v.rp_first;
+    if (second) *second = (uint64_t*)p->v.rp_second;
+    if (player) *player = p->v.rp_player;
+    if (pi) *pi = p->v.rp_pi;
+    if (z) *z = p->v.rp_z;
+    if (written) *written = (uint64_t*)p->v.rp_written;
+    return DM_OK;
+}

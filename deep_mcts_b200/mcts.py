@@ -1,0 +1,312 @@
+"""Reference-compatible ``MCTS`` / ``MCTSAgent`` on top of the CUDA tree pool.
+
+Keeps the constructor signature, methods and return types of reference deep_mcts/mcts.py
+(MCTS 57-245, MCTSAgent 248-300, play_random_mcts 303-316); the search itself runs in the
+kernels of csrc/tree.cu.  A plain ``MCTS`` is a pool of one tree (the batch-width-1 shim);
+``BatchedMCTS`` drives many trees in lock-step with the same semantics per tree.
+
+Evaluators and rollout policies
+  * ``state_evaluator=None`` / ``rollout_policy=None`` keep the reference meaning.
+  * The factories below return callables the engine recognises and runs entirely on the
+    device: ``uniform_state_evaluator`` (train.py:240-248), ``hashed_state_evaluator`` (test
+    evaluator), ``random_rollout_policy`` (``random.choice(legal_actions(s))``),
+    ``min_action_policy`` / ``max_action_policy``; a ``GameNet`` evaluator
+    (``net.evaluate`` / ``cached_state_evaluator(net)``) runs on the device network.
+  * Any other Python callable is honoured through the leaf-exchange path: the device
+    selects a leaf, the callable is evaluated on the host, the device expands and backs up.
+"""
+import random
+import time
+from typing import Callable, Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._engine import BoardManager, state_to_bits
+from .game import Action, GameManager, Player, State
+from .pool import TreePool, default_node_capacity
+from .tournament import Agent
+
+StateEvaluator = Callable[[State], Tuple[float, Sequence[float]]]
+RolloutPolicy = Callable[[State], Action]
+
+
+# ------------------------------------------------------------------ recognised callables
+def uniform_state_evaluator(manager: GameManager) -> StateEvaluator:
+    """(0.5, uniform over legal actions) -- the self-play evaluator before the first weight
+    transfer (reference train.py:240-248).  Runs on the device when given to MCTS."""
+
+    def evaluator(state):
+        legal = set(manager.legal_actions(state))
+        return 0.5, [1 / len(legal) if a in legal else 0.0 for a in range(manager.num_actions)]
+
+    evaluator._dm_eval_kind = _lib.DM_EVAL_UNIFORM
+    evaluator._dm_eval_salt = 0
+    return evaluator
+
+
+def hashed_state_evaluator(manager: GameManager, salt: int = 0) -> StateEvaluator:
+    """Deterministic synthetic evaluator built into the engine (parity tests)."""
+
+    def evaluator(state):
+        raise NotImplementedError("hashed_state_evaluator only runs on the device")
+
+    evaluator._dm_eval_kind = _lib.DM_EVAL_HASHED
+    evaluator._dm_eval_salt = int(salt)
+    return evaluator
+
+
+def random_rollout_policy(manager: GameManager) -> RolloutPolicy:
+    policy = lambda state: random.choice(manager.legal_actions(state))  # noqa: E731
+    policy._dm_rollout_kind = _lib.DM_ROLLOUT_RANDOM
+    return policy
+
+
+def min_action_policy(manager: GameManager) -> RolloutPolicy:
+    policy = lambda state: min(manager.legal_actions(state))  # noqa: E731
+    policy._dm_rollout_kind = _lib.DM_ROLLOUT_MIN_ACTION
+    return policy
+
+
+def max_action_policy(manager: GameManager) -> RolloutPolicy:
+    policy = lambda state: max(manager.legal_actions(state))  # noqa: E731
+    policy._dm_rollout_kind = _lib.DM_ROLLOUT_MAX_ACTION
+    return policy
+
+
+class Node:
+    """Read-only view of a tree node (reference mcts.py:27-54 field names)."""
+
+    __slots__ = ["children", "value_sum", "visits", "probability"]
+
+    def __init__(self, visits: int = 0, probability: float = -1.0) -> None:
+        self.visits = visits
+        self.value_sum = 0.0
+        self.probability = probability
+        self.children: Dict[Action, "Node"] = {}
+
+
+class BatchedMCTS:
+    """``n_trees`` independent searches with MCTS.step semantics per tree."""
+
+    def __init__(self, game_manager: BoardManager, n_trees: int, num_simulations: int,
+                 rollout_policy: Optional[RolloutPolicy], state_evaluator: Optional[StateEvaluator],
+                 sample_move_cutoff: int = 0, dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25,
+                 rollout_share: float = 1.0, max_nodes_per_tree: Optional[int] = None, seed: int = 0) -> None:
+        if rollout_policy is None and state_evaluator is None:
+            raise ValueError("Both rollout_policy and state_evaluator cannot be None")
+        self.game_manager = game_manager
+        self.num_simulations = num_simulations
+        self.rollout_policy = rollout_policy
+        self.state_evaluator = state_evaluator
+        self.sample_move_cutoff = sample_move_cutoff
+        self.dirichlet_alpha = dirichlet_alpha
+        self.dirichlet_factor = dirichlet_factor
+        self.rollout_share = rollout_share
+        sims_for_cap = num_simulations if num_simulations != float("inf") else 4096
+        cap = max_nodes_per_tree or default_node_capacity(game_manager, int(sims_for_cap))
+        self.pool = TreePool(game_manager, n_trees, cap, seed=seed)
+        self._classify()
+
+    # which device path serves the two callables
+    def _classify(self) -> None:
+        ev, ro = self.state_evaluator, self.rollout_policy
+        self._host_eval = None
+        self._host_rollout = None
+        self._net = None
+        if ev is None:
+            self._eval_kind, self._salt = _lib.DM_EVAL_NONE, 0
+        elif hasattr(ev, "_dm_eval_kind"):
+            self._eval_kind, self._salt = ev._dm_eval_kind, getattr(ev, "_dm_eval_salt", 0)
+        else:
+            self._eval_kind, self._salt = _lib.DM_EVAL_EXTERNAL, 0
+            net = getattr(ev, "_dm_net", None) or getattr(getattr(ev, "__self__", None), "_dm_net_self", None)
+            if net is not None and getattr(net, "on_device", False):
+                self._net = net
+            else:
+                self._host_eval = ev
+        if ro is None:
+            self._rollout_kind = _lib.DM_ROLLOUT_NONE
+        elif hasattr(ro, "_dm_rollout_kind"):
+            self._rollout_kind = ro._dm_rollout_kind
+        else:
+            # arbitrary Python policy: play it out on the host inside the leaf exchange
+            self._rollout_kind = _lib.DM_ROLLOUT_NONE
+            self._host_rollout = ro
+            if self._eval_kind != _lib.DM_EVAL_EXTERNAL:
+                self._host_eval = self.state_evaluator or None
+                self._eval_kind = _lib.DM_EVAL_EXTERNAL
+
+    def _configure(self, sims: int, alpha: Optional[float] = None) -> None:
+        self.pool.configure(sims, self._eval_kind, self._rollout_kind, self.sample_move_cutoff,
+                            self.dirichlet_alpha if alpha is None else alpha, self.dirichlet_factor,
+                            self.rollout_share, self._salt)
+
+    # ---- host leaf exchange -----------------------------------------------------------
+    def _host_evaluate(self, player, first, second):
+        m = self.game_manager
+        values, priors = [], []
+        for p, f, s in zip(player, first, second):
+            state = m._make_state(p, f, s)
+            if self._host_eval is not None:
+                value, probs = self._host_eval(state)
+                probs = [float(x) for x in probs]
+                assert len(probs) == m.num_actions
+            else:  # state_evaluator=None with a host rollout policy (mcts.py:202-212)
+                legal = set(m.legal_actions(state))
+                value, probs = 0.5, [1 / len(legal) if a in legal else 0.0 for a in range(m.num_actions)]
+            value = float(value)
+            if self._host_rollout is not None:
+                # evaluate_leaf's mixing rule (mcts.py:187-196) with the rollout played on the host
+                if self.state_evaluator is None:
+                    value = self._play_out(state)
+                elif not (self.rollout_share < 1.0 and random.random() >= self.rollout_share):
+                    value = (self._play_out(state) + value) / 2
+            values.append(value)
+            priors.append(probs)
+        return np.asarray(values, dtype=np.float64), np.asarray(priors, dtype=np.float64)
+
+    def _play_out(self, state) -> float:
+        m = self.game_manager
+        while not m.is_final_state(state):
+            state = m.generate_child_state(state, self._host_rollout(state))
+        return m.evaluate_final_state(state).value
+
+    # ---- one MCTS.step for every tree -------------------------------------------------
+    def run_simulations(self, sims: int, alpha: Optional[float] = None) -> None:
+        self._configure(sims, alpha)
+        self.pool.begin_step()
+        if self._eval_kind != _lib.DM_EVAL_EXTERNAL:
+            self.pool.search_local()
+        elif self._net is not None:
+            self._net.run_search(self.pool, sims)
+        else:
+            self.pool.step_external(self._host_evaluate, max_rounds=sims + 2)
+
+    def step(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(visits[n_trees, A], stats[n_trees, 2]) after ``num_simulations`` simulations per tree."""
+        self.run_simulations(int(self.num_simulations))
+        visits, stats = self.pool.root_visits()
+        self.pool.counters()  # surfaces capacity errors
+        return visits, stats
+
+    def advance(self, actions) -> None:
+        self.pool.advance(actions)
+
+    def reset(self, tree_ids=None) -> None:
+        self.pool.reset(tree_ids)
+
+
+class MCTS(BatchedMCTS):
+    """Drop-in for the reference's ``MCTS`` (one tree)."""
+
+    def __init__(self, game_manager: BoardManager, num_simulations: int, rollout_policy: Optional[RolloutPolicy],
+                 state_evaluator: Optional[StateEvaluator], sample_move_cutoff: int = 0,
+                 dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, rollout_share: float = 1.0,
+                 time_per_move: float = float("inf"), max_nodes_per_tree: Optional[int] = None,
+                 seed: int = 0) -> None:
+        super().__init__(game_manager, 1, num_simulations, rollout_policy, state_evaluator, sample_move_cutoff,
+                         dirichlet_alpha, dirichlet_factor, rollout_share, max_nodes_per_tree, seed)
+        self.time_per_move = time_per_move
+        self.state = game_manager.initial_game_state()
+
+    # ---- reference attributes -----------------------------------------------------------
+    @property
+    def root(self) -> Node:
+        order, count, root_visits = self.pool.root_children()
+        visits, _ = self.pool.root_visits()
+        node = Node(int(root_visits[0]))
+        for a in order[0, : int(count[0])]:
+            node.children[int(a)] = Node(int(visits[0, int(a)]))
+        return node
+
+    def step(self) -> Tuple[List[float], Tuple[int, int]]:
+        """One move's search (reference mcts.py:113-148)."""
+        with_exp = without_exp = 0
+        if self.time_per_move < float("inf"):
+            start = time.perf_counter()
+            budget = self.num_simulations
+            first_chunk = True
+            while time.perf_counter() - start < self.time_per_move and with_exp + without_exp < budget:
+                chunk = int(min(64, budget - (with_exp + without_exp)))
+                self.run_simulations(chunk, alpha=None if first_chunk else 0.0)
+                first_chunk = False
+                _, stats = self.pool.root_visits()
+                with_exp += int(stats[0, 0])
+                without_exp += int(stats[0, 1])
+        else:
+            self.run_simulations(int(self.num_simulations))
+            _, stats = self.pool.root_visits()
+            with_exp, without_exp = int(stats[0, 0]), int(stats[0, 1])
+        visits, _ = self.pool.root_visits()
+        self.pool.counters()
+        counts = [int(v) for v in visits[0]]
+        total = sum(counts)
+        return [c / total for c in counts], (with_exp, without_exp)
+
+    def advance(self, action: Action) -> None:
+        """``root = root.children[action]; state = child state`` (mcts.py:105-108)."""
+        self.pool.advance([int(action)])
+        self.state = self.game_manager.generate_child_state(self.state, int(action))
+
+    def observe(self, state) -> None:
+        """Re-root onto an observed state (MCTSAgent.play, mcts.py:267-283)."""
+        p, f, s = state_to_bits(state)
+        self.pool.observe([p], [f], [s])
+        self.state = state
+
+    def self_play(self) -> Iterable[Tuple[State, State, Action, Sequence[float]]]:
+        i = 0
+        while not self.game_manager.is_final_state(self.state):
+            probabilities, _ = self.step()
+            if i < self.sample_move_cutoff:
+                action = int(np.random.choice(len(probabilities), p=probabilities))
+            else:
+                action = int(np.argmax(probabilities))
+            old_state = self.state
+            self.advance(action)
+            i += 1
+            yield old_state, self.state, action, probabilities
+
+    def reset(self) -> None:
+        self.pool.reset()
+        self.state = self.game_manager.initial_game_state()
+
+
+class MCTSAgent(Agent):
+    """Tree-reusing player (reference mcts.py:248-300)."""
+
+    def __init__(self, mcts: MCTS, epsilon: float = 0.0,
+                 reset_fn: Optional[Callable[["MCTSAgent"], None]] = None) -> None:
+        self.mcts = mcts
+        self.epsilon = epsilon
+        self.current_game_simulation_stats: List[Tuple[int, int]] = []
+        self.simulation_stats = [self.current_game_simulation_stats]
+        self.reset_fn = reset_fn
+
+    def play(self, state) -> Action:
+        self.mcts.observe(state)
+        probabilities, simulations = self.mcts.step()
+        self.current_game_simulation_stats.append(simulations)
+        if self.epsilon > 0 and random.random() < self.epsilon:
+            action = int(np.random.choice(len(probabilities), p=probabilities))
+        else:
+            action = int(np.argmax(probabilities))
+        self.mcts.advance(action)
+        return action
+
+    def reset(self) -> None:
+        self.mcts.reset()
+        self.current_game_simulation_stats = []
+        self.simulation_stats.append(self.current_game_simulation_stats)
+        if self.reset_fn is not None:
+            self.reset_fn(self)
+
+
+def play_random_mcts(manager: BoardManager, num_simulations: int) -> None:
+    mcts = MCTS(manager, num_simulations, random_rollout_policy(manager), None)
+    next_state = mcts.state
+    for state, next_state, action, _ in mcts.self_play():
+        print(state, "\n", manager.action_str(action), "\n", sep="\n")
+    print(next_state)

@@ -1,0 +1,247 @@
+"""TreePool: thousands of independent MCTS trees resident in HBM, searched by CUDA kernels.
+
+This is the batched engine underneath the reference-compatible ``MCTS`` / ``MCTSAgent``
+classes (deep_mcts_b200/mcts.py).  One pool holds ``n_trees`` structure-of-arrays trees for
+one game on one GPU; every method is a thin wrapper over a ``dm_pool_*`` entry point of the
+C ABI (include/deepmcts_b200.h), which replaces reference deep_mcts/mcts.py:57-300.
+"""
+from typing import Callable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._engine import BoardManager, current_stream
+
+_TYPESTR = {torch.int64: "<i8", torch.uint8: "|u1", torch.int32: "<i4", torch.float32: "<f4",
+            torch.float64: "<f8"}
+
+
+class _DevicePtr:
+    """Exposes a library-owned device buffer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape: Tuple[int, ...], dtype: torch.dtype) -> None:
+        self.__cuda_array_interface__ = {
+            "shape": tuple(shape), "typestr": _TYPESTR[dtype], "data": (int(ptr), False), "version": 2,
+        }
+
+
+def wrap_device_buffer(ptr: int, shape, dtype: torch.dtype, device) -> torch.Tensor:
+    return torch.as_tensor(_DevicePtr(ptr, shape, dtype), device=device)
+
+
+def default_node_capacity(manager: BoardManager, num_simulations: int) -> int:
+    """Arena size per tree for a whole game without compaction: every simulation expands at most
+    one node (at most num_actions children), once per ply, plus the root expansions."""
+    plies = manager.board * manager.board + 8
+    per_move = (int(num_simulations) + 1) * manager.num_actions
+    return int(min(max(4096, plies * per_move // 2), 1 << 22))
+
+
+class TreePool:
+    def __init__(self, manager: BoardManager, n_trees: int, max_nodes_per_tree: int = 1 << 16, seed: int = 0,
+                 c_puct: float = 1.25) -> None:
+        self.manager = manager
+        self.n_trees = int(n_trees)
+        self.device = manager.device
+        self.num_actions = manager.num_actions
+        cfg = _lib.PoolConfig(manager.game_id, manager.board, self.n_trees, int(max_nodes_per_tree),
+                              self.device.index or 0, 0, float(c_puct), int(seed))
+        handle = _lib.c_void_p()
+        _lib.call("dm_pool_create", cfg, handle)
+        self._h = handle
+        self._search = None
+        self._noise = None
+        ptrs = [_lib.c_void_p() for _ in range(5)]
+        _lib.call("dm_pool_leaf_buffers", self._h, *ptrs)
+        T = self.n_trees
+        self.leaf_first = wrap_device_buffer(ptrs[0].value, (T,), torch.int64, self.device)
+        self.leaf_second = wrap_device_buffer(ptrs[1].value, (T,), torch.int64, self.device)
+        self.leaf_player = wrap_device_buffer(ptrs[2].value, (T,), torch.uint8, self.device)
+        self.leaf_tree = wrap_device_buffer(ptrs[3].value, (T,), torch.int32, self.device)
+        self.leaf_count = wrap_device_buffer(ptrs[4].value, (1,), torch.int32, self.device)
+        self._visits = torch.zeros((T, _lib.DM_MAX_ACTIONS), dtype=torch.int32, device=self.device)
+        self._stats = torch.zeros((T, 2), dtype=torch.int32, device=self.device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.call("dm_pool_destroy", self._h)
+            self._h = _lib.c_void_p()
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ configuration
+    def configure(self, num_simulations: int, eval_kind: int = _lib.DM_EVAL_EXTERNAL,
+                  rollout_kind: int = _lib.DM_ROLLOUT_NONE, sample_move_cutoff: int = 0,
+                  dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, rollout_share: float = 1.0,
+                  eval_salt: int = 0) -> None:
+        sc = _lib.SearchConfig(int(num_simulations), int(eval_kind), int(rollout_kind), int(sample_move_cutoff),
+                               float(dirichlet_alpha), float(dirichlet_factor), float(rollout_share),
+                               int(eval_salt))
+        _lib.call("dm_pool_configure", self._h, sc)
+        self._search = sc
+
+    def _ids(self, tree_ids):
+        if tree_ids is None:
+            return None, self.n_trees, 0
+        ids = torch.as_tensor(np.asarray(tree_ids, dtype=np.int32)).to(self.device)
+        return ids, ids.numel(), ids.data_ptr()
+
+    def _stream(self):
+        return current_stream()
+
+    # ----------------------------------------------------------------------- tree admin
+    def reset(self, tree_ids=None) -> None:
+        ids, n, ptr = self._ids(tree_ids)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_reset", self._h, ptr, n, self._stream())
+
+    def _state_args(self, player, first, second):
+        f = torch.from_numpy(np.asarray(first, dtype=np.uint64).view(np.int64)).to(self.device)
+        s = torch.from_numpy(np.asarray(second, dtype=np.uint64).view(np.int64)).to(self.device)
+        p = torch.from_numpy(np.asarray(player, dtype=np.uint8)).to(self.device)
+        return f, s, p
+
+    def set_root_states(self, player, first, second, tree_ids=None) -> None:
+        ids, n, ptr = self._ids(tree_ids)
+        f, s, p = self._state_args(player, first, second)
+        assert f.numel() == n
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_set_root_state", self._h, ptr, n, f.data_ptr(), s.data_ptr(), p.data_ptr(),
+                      self._stream())
+
+    def observe(self, player, first, second, tree_ids=None) -> None:
+        ids, n, ptr = self._ids(tree_ids)
+        f, s, p = self._state_args(player, first, second)
+        assert f.numel() == n
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_observe", self._h, ptr, n, f.data_ptr(), s.data_ptr(), p.data_ptr(), self._stream())
+
+    def set_noise(self, noise: Optional[np.ndarray]) -> None:
+        """Host-supplied Dirichlet noise [n_trees, <=65] in child order (parity tests); None = device RNG."""
+        if noise is None:
+            self._noise = None
+            _lib.call("dm_pool_set_noise", self._h, 0)
+            return
+        buf = np.zeros((self.n_trees, _lib.DM_MAX_ACTIONS), dtype=np.float64)
+        noise = np.asarray(noise, dtype=np.float64)
+        buf[:, : noise.shape[1]] = noise
+        self._noise = torch.from_numpy(buf).to(self.device)
+        _lib.call("dm_pool_set_noise", self._h, self._noise.data_ptr())
+
+    # --------------------------------------------------------------------------- search
+    def begin_step(self) -> None:
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_begin_step", self._h, self._stream())
+
+    def search_local(self) -> None:
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_search_local", self._h, self._stream())
+
+    def select(self) -> None:
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_select", self._h, self._stream())
+
+    def expand_backup(self, priors: torch.Tensor, values: torch.Tensor) -> None:
+        assert priors.is_cuda and values.is_cuda and priors.dtype == values.dtype
+        assert priors.is_contiguous() and values.is_contiguous()
+        is_f64 = 1 if priors.dtype == torch.float64 else 0
+        assert priors.dtype in (torch.float32, torch.float64)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_expand_backup", self._h, priors.data_ptr(), int(priors.shape[1]),
+                      values.data_ptr(), is_f64, self._stream())
+
+    def step_external(self, evaluate: Callable[[np.ndarray, np.ndarray, np.ndarray], Tuple[np.ndarray, np.ndarray]],
+                      max_rounds: Optional[int] = None) -> None:
+        """Run the armed simulations with a HOST evaluator: ``evaluate(player, first, second)``
+        returns (values[L] float64, priors[L, A] float64) for the L pending leaves.  This is the
+        injection point for arbitrary Python ``state_evaluator`` callables and for the
+        deterministic evaluators of the parity tests."""
+        rounds = 0
+        limit = max_rounds if max_rounds is not None else (self._search.num_simulations + 2)
+        while rounds < limit:
+            self.select()
+            n = int(self.leaf_count.item())
+            if n == 0:
+                break
+            p = self.leaf_player[:n].cpu().numpy()
+            f = self.leaf_first[:n].cpu().numpy().view(np.uint64)
+            s = self.leaf_second[:n].cpu().numpy().view(np.uint64)
+            values, priors = evaluate(p, f, s)
+            pri = np.zeros((self.n_trees, _lib.DM_MAX_ACTIONS), dtype=np.float64)
+            pri[:n, : self.num_actions] = np.asarray(priors, dtype=np.float64)[:, : self.num_actions]
+            val = np.zeros(self.n_trees, dtype=np.float64)
+            val[:n] = np.asarray(values, dtype=np.float64)
+            self.expand_backup(torch.from_numpy(pri).to(self.device), torch.from_numpy(val).to(self.device))
+            rounds += 1
+
+    # -------------------------------------------------------------------------- read-out
+    def root_visits(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(visits[n_trees, num_actions], stats[n_trees, 2]) of the last step (mcts.py:139-148)."""
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_root_visits", self._h, self._visits.data_ptr(), self._stats.data_ptr(),
+                      self._stream())
+        return self._visits[:, : self.num_actions].cpu().numpy(), self._stats.cpu().numpy()
+
+    def root_children(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        T = self.n_trees
+        order = torch.empty((T, _lib.DM_MAX_ACTIONS), dtype=torch.uint8, device=self.device)
+        count = torch.empty(T, dtype=torch.int32, device=self.device)
+        rv = torch.empty(T, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_root_children", self._h, order.data_ptr(), count.data_ptr(), rv.data_ptr(),
+                      self._stream())
+        return order.cpu().numpy(), count.cpu().numpy(), rv.cpu().numpy()
+
+    def advance(self, actions) -> None:
+        a = torch.from_numpy(np.asarray(actions, dtype=np.int32)).to(self.device)
+        assert a.numel() == self.n_trees
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_advance", self._h, a.data_ptr(), self._stream())
+
+    def states(self):
+        """(player, first, second, is_final, outcome) numpy arrays of the current roots."""
+        T = self.n_trees
+        f = torch.empty(T, dtype=torch.int64, device=self.device)
+        s = torch.empty(T, dtype=torch.int64, device=self.device)
+        p = torch.empty(T, dtype=torch.uint8, device=self.device)
+        fin = torch.empty(T, dtype=torch.uint8, device=self.device)
+        out = torch.empty(T, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_states", self._h, f.data_ptr(), s.data_ptr(), p.data_ptr(), fin.data_ptr(),
+                      out.data_ptr(), self._stream())
+        return (p.cpu().numpy(), f.cpu().numpy().view(np.uint64), s.cpu().numpy().view(np.uint64),
+                fin.cpu().numpy().astype(bool), out.cpu().numpy())
+
+    COUNTER_NAMES = ("simulations", "leaf_evals", "terminal_sims", "nodes_high_water", "games", "depth_sum",
+                     "children_scanned", "children_created", "capacity_errors", "moves", "rollout_plies",
+                     "invalid_actions")
+
+    def counters(self) -> dict:
+        out = (_lib.c_uint64 * 16)()
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_counters", self._h, out)
+        return {name: int(out[i]) for i, name in enumerate(self.COUNTER_NAMES)}
+
+    # ------------------------------------------------------------------------- self-play
+    def enable_selfplay(self, replay_capacity: int) -> None:
+        with torch.cuda.device(self.device):
+            _lib.call("dm_selfplay_enable", self._h, int(replay_capacity))
+        ptrs = [_lib.c_void_p() for _ in range(6)]
+        _lib.call("dm_selfplay_replay", self._h, *ptrs)
+        R = int(replay_capacity)
+        self.replay_capacity = R
+        self.replay_first = wrap_device_buffer(ptrs[0].value, (R,), torch.int64, self.device)
+        self.replay_second = wrap_device_buffer(ptrs[1].value, (R,), torch.int64, self.device)
+        self.replay_player = wrap_device_buffer(ptrs[2].value, (R,), torch.uint8, self.device)
+        self.replay_pi = wrap_device_buffer(ptrs[3].value, (R, _lib.DM_MAX_ACTIONS), torch.float32, self.device)
+        self.replay_z = wrap_device_buffer(ptrs[4].value, (R,), torch.float32, self.device)
+        self.replay_written = wrap_device_buffer(ptrs[5].value, (1,), torch.int64, self.device)
+
+    def selfplay_select(self) -> None:
+        with torch.cuda.device(self.device):
+            _lib.call("dm_selfplay_select", self._h, self._stream())

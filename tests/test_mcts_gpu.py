@@ -1,0 +1,186 @@
+"""GPU parity of the tree-search kernels: per-move root visit counts, (with, without) stats,
+child order and root visits must equal the reference's (golden fixture) and the oracle's,
+bit for bit, in exact mode with deterministic evaluators."""
+import json
+
+import numpy as np
+import pytest
+
+from oracle import evaluators as oev
+from oracle.games import make_game
+from oracle.mcts import OracleMCTS
+
+pytestmark = pytest.mark.gpu
+
+from test_games_gpu import manager_for  # noqa: E402
+
+
+def device_callables(manager, evaluator, rollout):
+    from deep_mcts_b200 import mcts as dm
+    ev = {None: None, "uniform": dm.uniform_state_evaluator(manager),
+          "hashed": dm.hashed_state_evaluator(manager, 0), "hashed7": dm.hashed_state_evaluator(manager, 7)}[evaluator]
+    ro = {None: None, "min": dm.min_action_policy(manager), "max": dm.max_action_policy(manager)}[rollout]
+    return ev, ro
+
+
+def check_move(m, mv):
+    dist, stats = m.step()
+    visits, _ = m.pool.root_visits()
+    order, count, root_visits = m.pool.root_children()
+    assert [int(v) for v in visits[0]] == mv["visits"]
+    assert list(stats) == mv["stats"]
+    assert [int(a) for a in order[0, :count[0]]] == mv["order"]
+    assert int(root_visits[0]) == mv["root_visits"]
+    total = sum(mv["visits"])
+    assert dist == [v / total for v in mv["visits"]]
+    root = m.root
+    assert list(root.children.keys()) == mv["order"] and root.visits == mv["root_visits"]
+
+
+def test_visit_counts_match_reference_fixture(golden_dir):
+    from deep_mcts_b200.mcts import MCTS
+    data = json.load(open(golden_dir / "mcts.json"))
+    for rec in data["games"]:
+        manager = manager_for(rec["game"], rec["grid"])
+        ev, ro = device_callables(manager, rec["evaluator"], rec["rollout"])
+        m = MCTS(manager, rec["sims"], ro, ev)
+        for mv in rec["moves"]:
+            check_move(m, mv)
+            m.advance(mv["action"])
+        assert manager.is_final_state(m.state)
+        assert manager.evaluate_final_state(m.state).value == rec["outcome"]
+
+
+def test_host_callable_evaluator_goes_through_leaf_exchange(golden_dir):
+    """An arbitrary Python state_evaluator / rollout_policy must give the same tree."""
+    from deep_mcts_b200._engine import state_to_bits
+    from deep_mcts_b200.mcts import MCTS
+    data = json.load(open(golden_dir / "mcts.json"))
+    picked = [r for r in data["games"] if (r["game"], r["grid"], r["evaluator"]) in
+              {("othello", 6, "hashed"), ("hex_with_swap", 5, "uniform"), ("tictactoe", 3, "hashed")}][:4]
+    picked += [r for r in data["games"] if r["rollout"] and r["game"] == "hex_with_swap"][:1]
+    assert picked
+    for rec in picked:
+        manager = manager_for(rec["game"], rec["grid"])
+        og = make_game(rec["game"], rec["grid"])
+        fn = {"uniform": oev.uniform, "hashed": oev.hashed, None: None}[rec["evaluator"]]
+        ev = (lambda state, fn=fn: fn(og, state_to_bits(state))) if fn else None
+        ro = None
+        if rec["rollout"]:
+            pick = min if rec["rollout"] == "min" else max
+            ro = lambda state, pick=pick: pick(manager.legal_actions(state))  # noqa: E731
+        m = MCTS(manager, rec["sims"], ro, ev)
+        for mv in rec["moves"]:
+            check_move(m, mv)
+            m.advance(mv["action"])
+
+
+def test_agent_rerooting_matches_reference_fixture(golden_dir):
+    from deep_mcts_b200.mcts import MCTS, MCTSAgent
+    data = json.load(open(golden_dir / "mcts.json"))
+    for rec in data["matches"]:
+        manager = manager_for(rec["game"], rec["grid"])
+        agents, logs = [], [iter(rec["log_a"]), iter(rec["log_b"])]
+        for sims, evk, rok in (rec["a"], rec["b"]):
+            ev, ro = device_callables(manager, evk, rok)
+            agents.append(MCTSAgent(MCTS(manager, sims, ro, ev)))
+        state = manager.initial_game_state()
+        turn = 0
+        while not manager.is_final_state(state):
+            agent = agents[turn]
+            agent.mcts.observe(state)
+            check_move(agent.mcts, next(logs[turn]))
+            # replay through the public agent API on a second copy is covered below; here advance manually
+            visits, _ = agent.mcts.pool.root_visits()
+            action = int(np.argmax(visits[0]))
+            agent.mcts.advance(action)
+            state = manager.generate_child_state(state, action)
+            turn ^= 1
+        assert manager.evaluate_final_state(state).value == rec["outcome"]
+
+
+def test_tournament_play_outcome_matches_reference(golden_dir):
+    from deep_mcts_b200.mcts import MCTS, MCTSAgent
+    from deep_mcts_b200.tournament import play
+    data = json.load(open(golden_dir / "mcts.json"))
+    rec = data["matches"][0]
+    manager = manager_for(rec["game"], rec["grid"])
+    agents = []
+    for sims, evk, rok in (rec["a"], rec["b"]):
+        ev, ro = device_callables(manager, evk, rok)
+        agents.append(MCTSAgent(MCTS(manager, sims, ro, ev)))
+    outcome = play((agents[0], agents[1]), manager)
+    assert outcome.value == rec["outcome"]
+    assert [list(s) for s in agents[0].simulation_stats[0]] == [m["stats"] for m in rec["log_a"]]
+
+
+@pytest.mark.parametrize("name,g,kind,sims", [("othello", 8, "hashed", 50), ("hex", 7, "uniform", 40),
+                                               ("hex_with_swap", 6, "hashed", 30), ("othello", 6, "uniform", 60)])
+def test_batched_trees_match_oracle(name, g, kind, sims):
+    """64 trees searched by one kernel launch per move, each from its own forced opening."""
+    from deep_mcts_b200 import mcts as dm
+    game = make_game(name, g)
+    manager = manager_for(name, g)
+    T, moves = 64, 6
+    ev = dm.uniform_state_evaluator(manager) if kind == "uniform" else dm.hashed_state_evaluator(manager, 0)
+    batch = dm.BatchedMCTS(manager, T, sims, None, ev)
+    refs = [OracleMCTS(game, sims, None, oev.uniform if kind == "uniform" else oev.hashed) for _ in range(T)]
+    rs = np.random.RandomState(0)
+    live = np.ones(T, bool)
+    for ply in range(moves):
+        visits, stats = batch.step()
+        actions = np.full(T, -1, np.int32)
+        for t, ref in enumerate(refs):
+            if not live[t]:
+                continue
+            _, ref_stats = ref.step()
+            assert [int(v) for v in visits[t]] == ref.root_visit_counts(), (t, ply)
+            assert tuple(stats[t]) == tuple(ref_stats)
+            legal = ref.root_children_actions()
+            a = legal[rs.randint(len(legal))] if ply < 3 else int(np.argmax(visits[t]))
+            ref.advance(a)
+            actions[t] = a
+            if game.is_final(ref.state):
+                live[t] = False
+        batch.advance(actions)
+    c = batch.pool.counters()
+    assert c["capacity_errors"] == 0 and c["simulations"] > 0
+
+
+def test_value_error_when_both_callables_missing():
+    from deep_mcts_b200.mcts import MCTS
+    with pytest.raises(ValueError):
+        MCTS(manager_for("tictactoe", 3), 10, None, None)
+
+
+def test_host_noise_dirichlet_matches_oracle():
+    """add_dirichlet_noise (mcts.py:233-241) with host-supplied noise, in child order."""
+    from deep_mcts_b200 import mcts as dm
+    game = make_game("othello", 6)
+    manager = manager_for("othello", 6)
+    m = dm.MCTS(manager, 40, None, dm.hashed_state_evaluator(manager), dirichlet_alpha=1.0)
+    ref = OracleMCTS(game, 40, None, oev.hashed, dirichlet_alpha=1.0)
+    rs = np.random.RandomState(4)
+    for _ in range(5):
+        n = len(game.children_order(ref.state))
+        noise = rs.dirichlet([1.0] * n)
+        m.pool.set_noise(noise[None, :])
+        dist, stats = m.step()
+        ref_dist, ref_stats = ref.step(noise=noise)
+        assert dist == ref_dist and tuple(stats) == tuple(ref_stats)
+        a = int(np.argmax(dist))
+        m.advance(a)
+        ref.advance(a)
+
+
+def test_device_dirichlet_and_random_rollouts_run():
+    """Stochastic device paths: sanity only (distributional parity is in test_games_gpu)."""
+    from deep_mcts_b200 import mcts as dm
+    manager = manager_for("hex_with_swap", 5)
+    m = dm.MCTS(manager, 64, dm.random_rollout_policy(manager), None, dirichlet_alpha=0.33, seed=3)
+    dist, stats = m.step()
+    assert abs(sum(dist) - 1.0) < 1e-12 and sum(stats) == 64
+    m2 = dm.MCTS(manager, 32, dm.random_rollout_policy(manager), dm.uniform_state_evaluator(manager),
+                 rollout_share=0.5)
+    dist, stats = m2.step()
+    assert sum(stats) == 32
