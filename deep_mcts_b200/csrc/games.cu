@@ -96,8 +96,9 @@ extern "C" int dm_game_num_actions(int game, int grid) {
 extern "C" int dm_game_initial(int game, int grid, int n, uint64_t* first, uint64_t* second, uint8_t* player,
                                void* stream) {
     DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_game_initial: unsupported game/grid");
-    DM_CHECK_ARG(n >= 0 && first && second && player, "dm_game_initial: bad arguments");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
     if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player, "dm_game_initial: bad arguments");
     k_game_initial<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_game_cfg(game, grid), n, (u64*)first,
                                                                       (u64*)second, player);
     DM_LAUNCH_CHECK();
@@ -108,8 +109,9 @@ extern "C" int dm_game_legal(int game, int grid, int n, const uint64_t* first, c
                              const uint8_t* player, uint8_t* list_dev, uint8_t* order_dev, int32_t* count_dev,
                              void* stream) {
     DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_game_legal: unsupported game/grid");
-    DM_CHECK_ARG(n >= 0 && first && second && player, "dm_game_legal: bad arguments");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
     if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player, "dm_game_legal: bad arguments");
     k_game_legal<<<(n + kWarpsPerBlock - 1) / kWarpsPerBlock, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
         make_game_cfg(game, grid), n, (const u64*)first, (const u64*)second, player, list_dev, order_dev,
         count_dev);
@@ -121,9 +123,10 @@ extern "C" int dm_game_child(int game, int grid, int n, const uint64_t* first, c
                              const uint8_t* player, const int32_t* action, uint64_t* ofirst, uint64_t* osecond,
                              uint8_t* oplayer, uint8_t* ok, void* stream) {
     DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_game_child: unsupported game/grid");
-    DM_CHECK_ARG(n >= 0 && first && second && player && action && ofirst && osecond && oplayer,
-                 "dm_game_child: bad arguments");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
     if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player && action && ofirst && osecond && oplayer,
+                 "dm_game_child: bad arguments");
     k_game_child<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_game_cfg(game, grid), n,
                                                                     (const u64*)first, (const u64*)second, player,
                                                                     action, (u64*)ofirst, (u64*)osecond, oplayer, ok);
@@ -134,8 +137,9 @@ extern "C" int dm_game_child(int game, int grid, int n, const uint64_t* first, c
 extern "C" int dm_game_status(int game, int grid, int n, const uint64_t* first, const uint64_t* second,
                               const uint8_t* player, uint8_t* is_final, float* outcome, void* stream) {
     DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_game_status: unsupported game/grid");
-    DM_CHECK_ARG(n >= 0 && first && second && player, "dm_game_status: bad arguments");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
     if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player, "dm_game_status: bad arguments");
     k_game_status<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_game_cfg(game, grid), n,
                                                                      (const u64*)first, (const u64*)second, player,
                                                                      is_final, outcome);
@@ -147,10 +151,11 @@ extern "C" int dm_game_rollout(int game, int grid, int n, const uint64_t* first,
                                const uint8_t* player, int rollout_kind, uint64_t seed, float* outcome,
                                int32_t* plies, void* stream) {
     DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_game_rollout: unsupported game/grid");
-    DM_CHECK_ARG(n >= 0 && first && second && player && outcome, "dm_game_rollout: bad arguments");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
+    if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player && outcome, "dm_game_rollout: bad arguments");
     DM_CHECK_ARG(rollout_kind >= DM_ROLLOUT_RANDOM && rollout_kind <= DM_ROLLOUT_MAX_ACTION,
                  "dm_game_rollout: bad rollout kind");
-    if (n == 0) return DM_OK;
     k_game_rollout<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(make_game_cfg(game, grid), n, (const u64*)first,
                                                                    (const u64*)second, player, rollout_kind,
                                                                    (u64)seed, outcome, plies);

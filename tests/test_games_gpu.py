@@ -67,11 +67,13 @@ def test_engine_matches_oracle_on_seeded_positions(name, g):
         assert float(out[i]) == game.outcome(s)
     # one random legal child per state + illegal-action detection
     rs = np.random.RandomState(3)
-    acts = np.array([lst[i, rs.randint(count[i])] for i in range(len(states))], np.int32)
+    has_move = count > 0  # a completely filled hex board has no legal action
+    acts = np.array([lst[i, rs.randint(count[i])] if has_move[i] else 0 for i in range(len(states))], np.int32)
     cp, cf, cs, ok = m.child_batch(player, first, second, acts)
-    assert ok.all()
+    assert np.array_equal(ok, has_move)
     for i, s in enumerate(states):
-        assert (int(cp[i]), int(cf[i]), int(cs[i])) == game.child(s, int(acts[i]))
+        if has_move[i]:
+            assert (int(cp[i]), int(cf[i]), int(cs[i])) == game.child(s, int(acts[i]))
     bad = np.full(len(states), game.num_actions + 3, np.int32)
     assert not m.child_batch(player, first, second, bad)[3].any()
 
