@@ -1,10 +1,358 @@
-// placeholder until the network kernels land (next commit)
-#include "common.cuh"
-#define DM_NET_STUB(name, ...) extern "C" int name(__VA_ARGS__) { dm_set_error(#name ": network kernels not built yet"); return DM_ERR_STATE; }
-DM_NET_STUB(dm_net_create, const dm_net_config*, dm_net**)
-DM_NET_STUB(dm_net_destroy, dm_net*)
-DM_NET_STUB(dm_net_set_tensor, dm_net*, const char*, const float*, int64_t)
-DM_NET_STUB(dm_net_finalize, dm_net*, void*)
-DM_NET_STUB(dm_net_evaluate, dm_net*, int, int, const int32_t*, const uint64_t*, const uint64_t*, const uint8_t*, float*, float*, void*)
-DM_NET_STUB(dm_net_forward, dm_net*, int, int, const uint64_t*, const uint64_t*, const uint8_t*, float*, float*, void*)
-DM_NET_STUB(dm_net_rollout_greedy, dm_net*, int, int, const uint64_t*, const uint64_t*, const uint8_t*, float*, void*)
+// dm_net_*: ConvolutionalNet leaf evaluation on the device (reference
+// deep_mcts/convolutionalnet.py:22-170 behind GameNet.evaluate / forward, gamenet.py:61-128).
+// precision 0 = fp32 CUDA cores (any architecture the reference can build),
+// precision 1 = bf16 tcgen05 trunk (channels == 128, num_residual >= 1).
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "net_fp32.cuh"
+// (net_fp32.cuh first: it defines live_count and the shared encode / heads kernels)
+#include "net_bf16.cuh"
+
+struct dm_net {
+    dm_net_config cfg;
+    GameCfg game;
+    RowGeom geom;
+    std::map<std::string, std::vector<float>> tensors;
+    std::vector<void*> allocations;
+    bool finalized = false;
+    bool bf16_ready = false;
+    int NA2 = 0;
+    size_t rows_total = 0;
+    // fp32 weights
+    float *conv1_w = nullptr, *conv1_b = nullptr;
+    std::vector<float*> trunk_w, trunk_b;
+    float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
+    float vconv_b = 0.f, vfc2_b = 0.f;
+    // bf16 weights
+    std::vector<__nv_bfloat16*> trunk_w16;
+    __nv_bfloat16* pfc_w16 = nullptr;
+    // activations
+    float *x0 = nullptr, *x1 = nullptr, *vplane = nullptr;
+    __nv_bfloat16 *a0 = nullptr, *a1 = nullptr, *t16 = nullptr;
+    // greedy rollout scratch
+    u64 *r_first = nullptr, *r_second = nullptr;
+    u8* r_player = nullptr;
+    float *r_value = nullptr, *r_probs = nullptr;
+    int* r_active = nullptr;
+};
+
+namespace {
+
+int net_alloc_bytes(dm_net* net, void** out, size_t bytes, bool zero) {
+    void* p = nullptr;
+    DM_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
+    net->allocations.push_back(p);
+    if (zero) DM_CUDA(cudaMemset(p, 0, bytes ? bytes : 16));
+    *out = p;
+    return DM_OK;
+}
+
+template <typename T>
+int net_upload(dm_net* net, T** out, const std::vector<T>& host) {
+    void* p = nullptr;
+    int rc = net_alloc_bytes(net, &p, host.size() * sizeof(T), false);
+    if (rc != DM_OK) return rc;
+    DM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = (T*)p;
+    return DM_OK;
+}
+
+#define DM_TRY(expr)                    \
+    do {                                \
+        int rc__ = (expr);              \
+        if (rc__ != DM_OK) return rc__; \
+    } while (0)
+
+void free_device(dm_net* net) {
+    for (void* p : net->allocations) cudaFree(p);
+    net->allocations.clear();
+    net->trunk_w.clear();
+    net->trunk_b.clear();
+    net->trunk_w16.clear();
+}
+
+// greedy rollout step: final states report their outcome and go inactive, others play argmax(probs)
+__global__ void k_greedy_step(GameCfg cfg, int n, u64* first, u64* second, u8* player, const float* probs,
+                              float* outcome, int* active) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    GState s;
+    s.first = first[i];
+    s.second = second[i];
+    s.player = player[i];
+    float o;
+    if (game_is_final(cfg, s, o)) {
+        outcome[i] = o;
+        return;
+    }
+    const float* p = probs + (size_t)i * DM_MAX_ACTIONS;
+    int best = 0;
+    float bv = p[0];
+    for (int a = 1; a < cfg.num_actions; ++a)
+        if (p[a] > bv) {  // np.argmax: first maximum
+            bv = p[a];
+            best = a;
+        }
+    if (!game_action_legal(cfg, s, best)) {  // degenerate all-zero policy: lowest legal action
+        bool extra;
+        u64 m = game_legal_mask(cfg, s, extra);
+        best = m ? (__ffsll((long long)m) - 1) : cfg.cells;
+    }
+    s = game_child(cfg, s, best);
+    first[i] = s.first;
+    second[i] = s.second;
+    player[i] = (u8)s.player;
+    atomicAdd(active, 1);
+}
+
+int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u64* first, const u64* second,
+                const u8* player, int mode, float* value_out, float* probs_out, cudaStream_t st) {
+    const GameCfg& g = net->game;
+    const int C = net->cfg.channels, R = net->cfg.num_residual, P0 = g.g * g.g, gp = g.g + 2;
+    const int L = 2 * R + 1;
+    size_t enc_smem = (size_t)(27 * C + C + netk::kEncodeBoards * 3 * gp * gp) * sizeof(float);
+    int enc_blocks = (n + netk::kEncodeBoards - 1) / netk::kEncodeBoards;
+    netk::HeadParams hp{net->pfc_b, net->vfc1_w, net->vfc1_b, net->vfc2_w, net->vfc2_b, net->cfg.hidden};
+    if (precision == 0) {
+        netk::k_encode_conv1<false><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player,
+                                                                       net->conv1_w, net->conv1_b, C, net->x0, nullptr, 0);
+        DM_LAUNCH_CHECK();
+        size_t conv_smem = (size_t)gp * gp * C * sizeof(float);
+        for (int i = 0; i < R; ++i) {
+            netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x0, net->trunk_w[2 * i],
+                                                           net->trunk_b[2 * i], nullptr, net->x1);
+            DM_LAUNCH_CHECK();
+            netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x1, net->trunk_w[2 * i + 1],
+                                                           net->trunk_b[2 * i + 1], net->x0, net->x0);
+            DM_LAUNCH_CHECK();
+        }
+        netk::k_vplane_f32<<<(n * P0 + 127) / 128, 128, 0, st>>>(P0, C, n, count_dev, net->x0, net->vconv_w,
+                                                                 net->vconv_b, net->vplane);
+        DM_LAUNCH_CHECK();
+        netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x0, net->trunk_w[L - 1],
+                                                       net->trunk_b[L - 1], nullptr, net->x1);
+        DM_LAUNCH_CHECK();
+        constexpr int kB = 4;
+        size_t hs = (size_t)kB * P0 * C * sizeof(float) + (size_t)kB * (net->NA2 + net->cfg.hidden) * sizeof(float);
+        netk::k_heads<float, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, first, second, player, net->x1,
+                                                                    net->pfc_w, C, net->NA2, net->vplane, hp, mode,
+                                                                    value_out, probs_out);
+        DM_LAUNCH_CHECK();
+        return DM_OK;
+    }
+    if (!net->bf16_ready) {
+        dm_set_error("bf16 path needs channels == 128 and num_residual >= 1");
+        return DM_ERR_INVALID;
+    }
+    netk::k_encode_conv1<true><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player, net->conv1_w,
+                                                                  net->conv1_b, C, nullptr, net->a0, net->rows_total);
+    DM_LAUNCH_CHECK();
+    const size_t conv_smem = netk::conv_smem_bytes(net->geom);
+    const int conv_blocks = (int)(((size_t)n * net->geom.P + netk::kRowsPerCta - 1) / netk::kRowsPerCta);
+    netk::ConvArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rows_total = net->rows_total;
+    a.n_boards = n;
+    a.count_dev = count_dev;
+    a.geom = net->geom;
+    for (int i = 0; i < R; ++i) {
+        a.in = net->a0; a.out = net->a1; a.out_nhwc = nullptr; a.residual = nullptr;
+        a.w = net->trunk_w16[2 * i]; a.bias = net->trunk_b[2 * i]; a.vhead_w = nullptr; a.vplane = nullptr;
+        netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+        DM_LAUNCH_CHECK();
+        a.in = net->a1; a.out = net->a0; a.residual = net->a0;
+        a.w = net->trunk_w16[2 * i + 1]; a.bias = net->trunk_b[2 * i + 1];
+        if (i == R - 1) {
+            a.vhead_w = net->vconv_w; a.vhead_b = net->vconv_b; a.vplane = net->vplane;
+        }
+        netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+        DM_LAUNCH_CHECK();
+    }
+    a.in = net->a0; a.out = nullptr; a.out_nhwc = net->t16; a.residual = nullptr;
+    a.w = net->trunk_w16[L - 1]; a.bias = net->trunk_b[L - 1]; a.vhead_w = nullptr; a.vplane = nullptr;
+    netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+    DM_LAUNCH_CHECK();
+    constexpr int kB = 8;
+    size_t hs = (size_t)kB * P0 * C * sizeof(__nv_bfloat16) + (size_t)kB * (net->NA2 + net->cfg.hidden) * sizeof(float);
+    netk::k_heads<__nv_bfloat16, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, first, second, player,
+                                                                        net->t16, net->pfc_w16, C, net->NA2,
+                                                                        net->vplane, hp, mode, value_out, probs_out);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+}  // namespace
+
+extern "C" int dm_net_create(const dm_net_config* cfg, dm_net** out) {
+    DM_CHECK_ARG(cfg && out, "dm_net_create: null argument");
+    DM_CHECK_ARG(game_cfg_valid(cfg->game, cfg->grid), "dm_net_create: unsupported game/grid");
+    DM_CHECK_ARG(cfg->channels >= 1 && cfg->channels <= 512 && cfg->num_residual >= 0 && cfg->hidden >= 1 &&
+                     cfg->max_batch >= 1,
+                 "dm_net_create: bad architecture");
+    dm_net* net = new (std::nothrow) dm_net();
+    DM_CHECK_ARG(net, "dm_net_create: out of host memory");
+    net->cfg = *cfg;
+    net->game = make_game_cfg(cfg->game, cfg->grid);
+    net->geom = RowGeom::make(net->game.g);
+    *out = net;
+    return DM_OK;
+}
+
+extern "C" int dm_net_destroy(dm_net* net) {
+    if (!net) return DM_OK;
+    cudaSetDevice(net->cfg.device);
+    free_device(net);
+    delete net;
+    return DM_OK;
+}
+
+extern "C" int dm_net_set_tensor(dm_net* net, const char* key, const float* host_data, int64_t numel) {
+    DM_CHECK_ARG(net && key && host_data && numel >= 0, "dm_net_set_tensor: bad arguments");
+    net->tensors[key] = std::vector<float>(host_data, host_data + numel);
+    net->finalized = false;
+    return DM_OK;
+}
+
+extern "C" int dm_net_finalize(dm_net* net, void* stream) {
+    DM_CHECK_ARG(net, "dm_net_finalize: null net");
+    DM_CUDA(cudaSetDevice(net->cfg.device));
+    DM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    const int C = net->cfg.channels, R = net->cfg.num_residual, H = net->cfg.hidden, g = net->game.g;
+    const int A = net->game.num_actions, P0 = g * g, n = net->cfg.max_batch;
+    HostWeights hw;
+    std::string err;
+    if (!build_host_weights(net->tensors, C, R, H, g, A, hw, err)) {
+        dm_set_error("dm_net_finalize: " + err);
+        return DM_ERR_INVALID;
+    }
+    DM_CUDA(cudaDeviceSynchronize());
+    free_device(net);
+    net->NA2 = hw.NA2;
+    DM_TRY(net_upload(net, &net->conv1_w, hw.conv1_w));
+    DM_TRY(net_upload(net, &net->conv1_b, hw.conv1_b));
+    const int L = 2 * R + 1;
+    net->trunk_w.assign(L, nullptr);
+    net->trunk_b.assign(L, nullptr);
+    for (int l = 0; l < L; ++l) {
+        DM_TRY(net_upload(net, &net->trunk_w[l], hw.trunk_w[l]));
+        DM_TRY(net_upload(net, &net->trunk_b[l], hw.trunk_b[l]));
+    }
+    DM_TRY(net_upload(net, &net->vconv_w, hw.vconv_w));
+    net->vconv_b = hw.vconv_b;
+    DM_TRY(net_upload(net, &net->vfc1_w, hw.vfc1_w));
+    DM_TRY(net_upload(net, &net->vfc1_b, hw.vfc1_b));
+    DM_TRY(net_upload(net, &net->vfc2_w, hw.vfc2_w));
+    net->vfc2_b = hw.vfc2_b;
+    DM_TRY(net_upload(net, &net->pfc_w, hw.pfc_w));
+    DM_TRY(net_upload(net, &net->pfc_b, hw.pfc_b));
+    size_t act = (size_t)n * P0 * C;
+    DM_TRY(net_alloc_bytes(net, (void**)&net->x0, act * sizeof(float), false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->x1, act * sizeof(float), false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->vplane, (size_t)n * P0 * sizeof(float), true));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_first, (size_t)n * 8, false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_second, (size_t)n * 8, false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_player, (size_t)n, false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_value, (size_t)n * 4, false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_probs, (size_t)n * DM_MAX_ACTIONS * 4, false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_active, 16, true));
+    net->bf16_ready = false;
+    if (C == netk::kC && R >= 1) {
+        net->trunk_w16.assign(L, nullptr);
+        for (int l = 0; l < L; ++l) {
+            std::vector<__nv_bfloat16> packed;
+            pack_trunk_bf16(hw.trunk_w[l], C, packed);
+            DM_TRY(net_upload(net, &net->trunk_w16[l], packed));
+        }
+        std::vector<__nv_bfloat16> p16(hw.pfc_w.size());
+        for (size_t i = 0; i < p16.size(); ++i) p16[i] = __float2bfloat16(hw.pfc_w[i]);
+        DM_TRY(net_upload(net, &net->pfc_w16, p16));
+        net->rows_total = netk::conv_rows_total(net->geom, n);
+        size_t abytes = (size_t)netk::kChunks * net->rows_total * 16;
+        // zeroed once: pad rows are never written afterwards and must stay zero
+        DM_TRY(net_alloc_bytes(net, (void**)&net->a0, abytes, true));
+        DM_TRY(net_alloc_bytes(net, (void**)&net->a1, abytes, true));
+        DM_TRY(net_alloc_bytes(net, (void**)&net->t16, act * sizeof(__nv_bfloat16), true));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::conv_smem_bytes(net->geom)));
+        size_t hs = (size_t)8 * P0 * C * sizeof(__nv_bfloat16) + (size_t)8 * (hw.NA2 + H) * sizeof(float);
+        DM_CUDA(cudaFuncSetAttribute(netk::k_heads<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)hs));
+        net->bf16_ready = true;
+    }
+    {
+        const int gp = g + 2;
+        size_t conv_smem = (size_t)gp * gp * C * sizeof(float);
+        size_t hs = (size_t)4 * P0 * C * sizeof(float) + (size_t)4 * (hw.NA2 + H) * sizeof(float);
+        size_t enc = (size_t)(27 * C + C + netk::kEncodeBoards * 3 * gp * gp) * sizeof(float);
+        DM_CHECK_ARG(conv_smem <= 227 * 1024 && hs <= 227 * 1024 && enc <= 227 * 1024,
+                     "dm_net_finalize: architecture too large for the shared-memory staged kernels");
+        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_f32, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv_smem));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_heads<float, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc));
+    }
+    DM_CUDA(cudaDeviceSynchronize());
+    net->finalized = true;
+    return DM_OK;
+}
+
+static int check_eval_args(dm_net* net, int precision, int n, const void* a, const void* b, const void* c,
+                           const void* d, const void* e) {
+    DM_CHECK_ARG(net, "dm_net: null net");
+    if (!net->finalized) {
+        dm_set_error("dm_net: call dm_net_finalize after setting the tensors");
+        return DM_ERR_STATE;
+    }
+    DM_CHECK_ARG(precision == 0 || precision == 1, "dm_net: precision must be 0 (fp32) or 1 (bf16)");
+    DM_CHECK_ARG(n >= 0 && n <= net->cfg.max_batch, "dm_net: batch larger than max_batch");
+    if (n == 0) return 1;
+    DM_CHECK_ARG(a && b && c && d && e, "dm_net: null device pointer");
+    return DM_OK;
+}
+
+extern "C" int dm_net_evaluate(dm_net* net, int precision, int n, const int32_t* count_dev, const uint64_t* first,
+                               const uint64_t* second, const uint8_t* player, float* value, float* probs,
+                               void* stream) {
+    int rc = check_eval_args(net, precision, n, first, second, player, value, probs);
+    if (rc != DM_OK) return rc < 0 ? rc : DM_OK;
+    return run_forward(net, precision, n, count_dev, (const u64*)first, (const u64*)second, player, 0, value, probs,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int dm_net_forward(dm_net* net, int precision, int n, const uint64_t* first, const uint64_t* second,
+                              const uint8_t* player, float* value, float* logits, void* stream) {
+    int rc = check_eval_args(net, precision, n, first, second, player, value, logits);
+    if (rc != DM_OK) return rc < 0 ? rc : DM_OK;
+    return run_forward(net, precision, n, nullptr, (const u64*)first, (const u64*)second, player, 1, value, logits,
+                       (cudaStream_t)stream);
+}
+
+extern "C" int dm_net_rollout_greedy(dm_net* net, int precision, int n, const uint64_t* first,
+                                     const uint64_t* second, const uint8_t* player, float* outcome, void* stream) {
+    int rc = check_eval_args(net, precision, n, first, second, player, outcome, outcome);
+    if (rc != DM_OK) return rc < 0 ? rc : DM_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    DM_CUDA(cudaMemcpyAsync(net->r_first, first, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    DM_CUDA(cudaMemcpyAsync(net->r_second, second, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    DM_CUDA(cudaMemcpyAsync(net->r_player, player, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    const int max_plies = 2 * net->game.cells + 4;
+    for (int ply = 0; ply <= max_plies; ++ply) {
+        rc = run_forward(net, precision, n, nullptr, net->r_first, net->r_second, net->r_player, 0, net->r_value,
+                         net->r_probs, st);
+        if (rc != DM_OK) return rc;
+        DM_CUDA(cudaMemsetAsync(net->r_active, 0, sizeof(int), st));
+        k_greedy_step<<<(n + 127) / 128, 128, 0, st>>>(net->game, n, net->r_first, net->r_second, net->r_player,
+                                                       net->r_probs, outcome, net->r_active);
+        DM_LAUNCH_CHECK();
+        int active = 0;
+        DM_CUDA(cudaMemcpyAsync(&active, net->r_active, sizeof(int), cudaMemcpyDeviceToHost, st));
+        DM_CUDA(cudaStreamSynchronize(st));
+        if (active == 0) return DM_OK;
+    }
+    dm_set_error("dm_net_rollout_greedy: games did not finish");
+    return DM_ERR_STATE;
+}

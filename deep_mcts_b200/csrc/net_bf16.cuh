@@ -1,0 +1,279 @@
+// bf16 trunk of ConvolutionalNet on the 5th-generation tensor cores: every 3x3, 128 -> 128
+// convolution (+ folded BN, + residual, + ReLU) is an implicit GEMM issued with tcgen05.mma,
+// accumulating in TMEM.  (reference deep_mcts/convolutionalnet.py:91-129, 132-153; these
+// seven layers are 99% of the network's FLOPs.)
+//
+// Formulation.  Activations live in HBM as padded flat rows (RowGeom): row = one board cell or a
+// zero pad, 128 channels split into 16 chunks of 8 bf16 (16 bytes), stored chunk-major:
+//     act[(kc * rows_total + row) * 8 + j]
+// which is exactly the K-major, no-swizzle UMMA operand layout with 16-byte row pitch
+// (SBO = 128 B per 8-row group, LBO = rows * 16 B per K chunk).  Because row pitch is uniform,
+// the A operand of tap (dy, dx) is the SAME shared-memory image read from a start address
+// shifted by (dy*Wp + dx) rows -- no im2col copies, one activation load per CTA.
+//   GEMM per CTA: M = 4 tiles x 128 rows, N = 128, K = 9 taps x 128 channels.
+//   A  : 512 + 2*halo rows x 128 ch, one cp.async.bulk per channel chunk (16 copies)
+//   B  : per tap a pre-packed 32 KB weight image, double buffered (cp.async.bulk)
+//   D  : 4 x (128 lanes x 128 columns) fp32 = all 512 TMEM columns
+// Warp roles: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
+// epilogue (tcgen05.ld -> bias / residual / ReLU -> bf16 -> coalesced 16-byte stores).
+#pragma once
+#include <cuda_bf16.h>
+
+#include "net_pack.cuh"
+
+namespace netk {
+
+constexpr int kC = 128;               // channels (N and the K chunking are specialised for 128)
+constexpr int kChunks = kC / 8;       // 16-byte channel chunks
+constexpr int kTileM = 128;           // rows per tcgen05.mma (M)
+constexpr int kTilesPerCta = 4;       // accumulators per CTA
+constexpr int kRowsPerCta = kTileM * kTilesPerCta;
+constexpr int kStages = 2;            // weight stages
+constexpr int kStageBytes = kC * kC * 2;  // one tap: 32 KB
+constexpr int kConvThreads = 192;
+
+struct ConvArgs {
+    const __nv_bfloat16* in;        // chunked rows
+    __nv_bfloat16* out;             // chunked rows, or null
+    __nv_bfloat16* out_nhwc;        // dense [board][pos][128] (policy conv), or null
+    const __nv_bfloat16* residual;  // chunked rows, or null (may alias out)
+    const __nv_bfloat16* w;         // [9][16][128][8]
+    const float* bias;              // [128]
+    const float* vhead_w;           // [128] or null: also emit the value-head 1x1 conv
+    float vhead_b;
+    float* vplane;                  // [n][g*g]
+    size_t rows_total;
+    int n_boards;
+    const int* count_dev;
+    RowGeom geom;
+};
+
+__host__ __device__ inline int conv_a_rows(const RowGeom& geom) { return kRowsPerCta + 2 * geom.halo; }
+inline size_t conv_smem_bytes(const RowGeom& geom) {
+    return 1024 + (size_t)kChunks * conv_a_rows(geom) * 16 + (size_t)kStages * kStageBytes + 2 * kC * sizeof(float) + 128;
+}
+// rows a buffer must hold for n boards: front halo + whole CTA tiles + back halo
+inline size_t conv_rows_total(const RowGeom& geom, int n_boards) {
+    size_t body = ((size_t)n_boards * geom.P + kRowsPerCta - 1) / kRowsPerCta * kRowsPerCta;
+    return body + 2 * (size_t)geom.halo;
+}
+
+// ---- PTX wrappers ------------------------------------------------------------------------
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u32 bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u32 bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u32 bar, u32 parity) {
+    u32 done = 0;
+    unsigned long long spins = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (++spins > (1ull << 26)) __trap();  // never hang the GPU: fail the launch instead
+    }
+}
+__device__ __forceinline__ void bulk_g2s(u32 dst, const void* src, u32 bytes, u32 bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(u32 bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(u32 tmem_d, u64 adesc, u64 bdesc, u32 idesc, u32 accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld32(u32 taddr, u32 (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+// start address, leading (K-chunk) byte offset, stride (8-row group) byte offset, all >> 4; version 1.
+__device__ __forceinline__ u64 umma_desc(u32 saddr, u32 lbo_bytes, u32 sbo_bytes) {
+    return (u64)((saddr & 0x3FFFFu) >> 4) | ((u64)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+           ((u64)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
+constexpr u32 kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kC >> 3) << 17) | ((u32)(kTileM >> 4) << 24);
+
+__device__ __forceinline__ u32 pack_bf16(float a, float b) {
+    __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<u32*>(&p);
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
+    extern __shared__ unsigned char smem_raw[];
+    const RowGeom geom = args.geom;
+    const int a_rows = conv_a_rows(geom);
+    const int live = live_count(args.count_dev, args.n_boards);
+    const size_t tile_row0 = (size_t)blockIdx.x * kRowsPerCta;  // board-space row of this CTA's first output row
+    if ((int)(tile_row0 / geom.P) >= live) return;              // nothing live in this CTA (block-uniform)
+
+    // carve shared memory (1024-byte aligned base)
+    unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
+    unsigned char* s_a = base;                                    // [16][a_rows][16 B]
+    unsigned char* s_b = s_a + (size_t)kChunks * a_rows * 16;     // [2][32 KB]
+    float* s_bias = (float*)(s_b + (size_t)kStages * kStageBytes);
+    float* s_vw = s_bias + kC;
+    u64* s_bar = (u64*)(s_vw + kC);  // full[2], empty[2], a_full, acc_full
+    u32* s_tmem = (u32*)(s_bar + 8);
+    const u32 bar_full0 = smem_u32(&s_bar[0]), bar_empty0 = smem_u32(&s_bar[2]);
+    const u32 bar_a = smem_u32(&s_bar[4]), bar_acc = smem_u32(&s_bar[5]);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kC; i += blockDim.x) {
+        s_bias[i] = args.bias[i];
+        s_vw[i] = args.vhead_w ? args.vhead_w[i] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(bar_full0 + 8 * s, 1);
+            mbar_init(bar_empty0 + 8 * s, 1);
+        }
+        mbar_init(bar_a, 1);
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- producer: activations once, then the nine weight taps through two stages
+            const u32 a_chunk_bytes = (u32)a_rows * 16;
+            mbar_expect_tx(bar_a, a_chunk_bytes * kChunks);
+            for (int kc = 0; kc < kChunks; ++kc)
+                bulk_g2s(smem_u32(s_a + (size_t)kc * a_chunk_bytes),
+                         args.in + ((size_t)kc * args.rows_total + tile_row0) * 8, a_chunk_bytes, bar_a);
+            for (int tap = 0; tap < 9; ++tap) {
+                int st = tap % kStages;
+                if (tap >= kStages) mbar_wait(bar_empty0 + 8 * st, ((tap / kStages) - 1) & 1);
+                mbar_expect_tx(bar_full0 + 8 * st, kStageBytes);
+                bulk_g2s(smem_u32(s_b + (size_t)st * kStageBytes), args.w + (size_t)tap * kC * kC, kStageBytes,
+                         bar_full0 + 8 * st);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            const u32 lbo_a = (u32)a_rows * 16, lbo_b = kC * 16, sbo = 128;
+            mbar_wait(bar_a, 0);
+            for (int tap = 0; tap < 9; ++tap) {
+                int st = tap % kStages;
+                mbar_wait(bar_full0 + 8 * st, (tap / kStages) & 1);
+                tc_fence_after();
+                const int shift = (tap / 3 - 1) * geom.Wp + (tap % 3 - 1);  // rows
+                const u32 b_addr = smem_u32(s_b + (size_t)st * kStageBytes);
+#pragma unroll
+                for (int tile = 0; tile < kTilesPerCta; ++tile) {
+                    const u32 a_addr = smem_u32(s_a) + (u32)(geom.halo + tile * kTileM + shift) * 16;
+#pragma unroll
+                    for (int k16 = 0; k16 < kC / 16; ++k16) {
+                        u64 ad = umma_desc(a_addr + (u32)(2 * k16) * lbo_a, lbo_a, sbo);
+                        u64 bd = umma_desc(b_addr + (u32)(2 * k16) * lbo_b, lbo_b, sbo);
+                        tc_mma_bf16(tmem_base + (u32)(tile * kC), ad, bd, kIdescBf16, (tap | k16) ? 1u : 0u);
+                    }
+                }
+                tc_commit(bar_empty0 + 8 * st);  // frees this weight stage when the MMAs retire
+            }
+            tc_commit(bar_acc);
+        }
+    } else {
+        // ---- epilogue: warps 2..5 own TMEM lane quarters (warp % 4)
+        const int quarter = warp & 3;
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int g = geom.g, P0 = g * g;
+        for (int tile = 0; tile < kTilesPerCta; ++tile) {
+            const size_t q = tile_row0 + (size_t)tile * kTileM + quarter * 32 + lane;  // board-space row
+            const size_t m = q + geom.halo;                                              // buffer row
+            const int b = (int)(q / geom.P), rem = (int)(q % geom.P);
+            const int y = rem / geom.Wp, x = rem % geom.Wp;
+            const bool valid = (b < live) && (y < g) && (x < g);
+            float vacc = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < kC / 32; ++cc) {
+                u32 v[32];
+                tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)(tile * kC + cc * 32), v);
+                tc_wait_ld();
+                if (!valid) continue;
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) + s_bias[cc * 32 + j];
+                if (args.residual) {
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        uint4 r = *reinterpret_cast<const uint4*>(
+                            args.residual + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8);
+                        const u32 rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            f[c4 * 8 + 2 * j] += __uint_as_float(rw[j] << 16);
+                            f[c4 * 8 + 2 * j + 1] += __uint_as_float(rw[j] & 0xffff0000u);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    f[j] = fmaxf(f[j], 0.f);
+                    vacc = fmaf(f[j], s_vw[cc * 32 + j], vacc);
+                }
+#pragma unroll
+                for (int c4 = 0; c4 < 4; ++c4) {
+                    uint4 o;
+                    o.x = pack_bf16(f[c4 * 8 + 0], f[c4 * 8 + 1]);
+                    o.y = pack_bf16(f[c4 * 8 + 2], f[c4 * 8 + 3]);
+                    o.z = pack_bf16(f[c4 * 8 + 4], f[c4 * 8 + 5]);
+                    o.w = pack_bf16(f[c4 * 8 + 6], f[c4 * 8 + 7]);
+                    if (args.out)
+                        *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
+                    if (args.out_nhwc)
+                        *reinterpret_cast<uint4*>(args.out_nhwc + ((size_t)b * P0 + y * g + x) * kC + cc * 32 + c4 * 8) = o;
+                }
+            }
+            if (valid && args.vhead_w) args.vplane[(size_t)b * P0 + y * g + x] = fmaxf(vacc + args.vhead_b, 0.f);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+}  // namespace netk

@@ -1,0 +1,137 @@
+"""DeviceNet: the CUDA inference engine for ConvolutionalNet (wraps dm_net_* of the C ABI).
+
+Packs a reference-format state_dict (BatchNorm folded, weights re-laid for the kernels) and
+evaluates batches of bitboard states entirely on the device:
+``states -> planes -> conv trunk -> heads -> tanh/sign/softmax/mask`` (reference
+deep_mcts/gamenet.py:61-85 over convolutionalnet.py:53-68).  precision "fp32" is the
+CUDA-core path (1e-5 parity), "bf16" the tcgen05 tensor-core path (1e-2 parity, channels=128).
+"""
+from typing import Dict, Optional, Tuple
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._engine import BoardManager, current_stream
+
+PRECISIONS = {"fp32": 0, "bf16": 1}
+
+
+class DeviceNet:
+    on_device = True
+
+    def __init__(self, manager: BoardManager, channels: int, num_residual: int, hidden: int, max_batch: int = 4096,
+                 precision: Optional[str] = None) -> None:
+        self.manager = manager
+        self.device = manager.device
+        self.channels, self.num_residual, self.hidden = int(channels), int(num_residual), int(hidden)
+        self.max_batch = int(max_batch)
+        if precision is None:
+            precision = "bf16" if (self.channels == 128 and self.num_residual >= 1) else "fp32"
+        if precision not in PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(PRECISIONS)}")
+        self.precision = precision
+        cfg = _lib.NetConfig(manager.game_id, manager.board, self.channels, self.num_residual, self.hidden,
+                             self.device.index or 0, self.max_batch, 0)
+        handle = _lib.c_void_p()
+        _lib.call("dm_net_create", cfg, handle)
+        self._h = handle
+        self._loaded = False
+        A = _lib.DM_MAX_ACTIONS
+        self._value = torch.zeros(self.max_batch, dtype=torch.float32, device=self.device)
+        self._probs = torch.zeros((self.max_batch, A), dtype=torch.float32, device=self.device)
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h.value:
+            _lib.call("dm_net_destroy", self._h)
+            self._h = _lib.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -------------------------------------------------------------------------- weights
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Upload a reference-format state_dict and (re)pack it for the kernels."""
+        for key, tensor in state_dict.items():
+            if key.endswith("num_batches_tracked"):
+                continue
+            host = np.ascontiguousarray(tensor.detach().to("cpu", torch.float32).numpy())
+            _lib.call("dm_net_set_tensor", self._h, key.encode(), host.ctypes.data, host.size)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_finalize", self._h, current_stream())
+        self._loaded = True
+
+    # ------------------------------------------------------------------------ inference
+    def _check(self, n: int) -> None:
+        if not self._loaded:
+            raise RuntimeError("DeviceNet has no weights: call load_state_dict first")
+        if n > self.max_batch:
+            raise ValueError(f"batch {n} exceeds max_batch {self.max_batch}")
+
+    def evaluate_device(self, first: torch.Tensor, second: torch.Tensor, player: torch.Tensor, n: int,
+                        count_dev: Optional[torch.Tensor] = None, precision: Optional[str] = None
+                        ) -> Tuple[torch.Tensor, torch.Tensor]:
+        """GameNet.evaluate for ``n`` device-resident states; returns device tensors
+        (value[n] absolute in [0,1], probs[n, 65]) that stay valid until the next call."""
+        self._check(n)
+        prec = PRECISIONS[precision or self.precision]
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_evaluate", self._h, prec, int(n), count_dev.data_ptr() if count_dev is not None else 0,
+                      first.data_ptr(), second.data_ptr(), player.data_ptr(), self._value.data_ptr(),
+                      self._probs.data_ptr(), current_stream())
+        return self._value, self._probs
+
+    def _upload(self, player, first, second):
+        f = torch.from_numpy(np.asarray(first, dtype=np.uint64).view(np.int64)).to(self.device)
+        s = torch.from_numpy(np.asarray(second, dtype=np.uint64).view(np.int64)).to(self.device)
+        p = torch.from_numpy(np.asarray(player, dtype=np.uint8)).to(self.device)
+        return f, s, p
+
+    def evaluate(self, player, first, second, precision: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """Host arrays in, host arrays out: (value[n], probs[n, num_actions])."""
+        f, s, p = self._upload(player, first, second)
+        n = f.numel()
+        value, probs = self.evaluate_device(f, s, p, n, None, precision)
+        return value[:n].cpu().numpy(), probs[:n, : self.manager.num_actions].cpu().numpy()
+
+    def forward(self, player, first, second, precision: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
+        """GameNet.forward: raw value (pre-tanh) and logits (Hex un-transpose applied)."""
+        f, s, p = self._upload(player, first, second)
+        n = f.numel()
+        self._check(n)
+        prec = PRECISIONS[precision or self.precision]
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_forward", self._h, prec, n, f.data_ptr(), s.data_ptr(), p.data_ptr(),
+                      self._value.data_ptr(), self._probs.data_ptr(), current_stream())
+        return self._value[:n].cpu().numpy(), self._probs[:n, : self.manager.num_actions].cpu().numpy()
+
+    def rollout_greedy(self, player, first, second, precision: Optional[str] = None) -> np.ndarray:
+        """Outcome of playing argmax of the masked policy from every state
+        (reference deep_mcts/evaluate_complex_rollouts.py:57-59)."""
+        f, s, p = self._upload(player, first, second)
+        n = f.numel()
+        self._check(n)
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_rollout_greedy", self._h, PRECISIONS[precision or self.precision], n, f.data_ptr(),
+                      s.data_ptr(), p.data_ptr(), out.data_ptr(), current_stream())
+        return out.cpu().numpy()
+
+    # --------------------------------------------------------------------------- search
+    def search_round(self, pool, selfplay: bool = False) -> None:
+        """One select -> evaluate -> expand/backup round for every tree of the pool (no host sync)."""
+        if selfplay:
+            pool.selfplay_select()
+        else:
+            pool.select()
+        value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.n_trees,
+                                            pool.leaf_count)
+        pool.expand_backup(probs, value)
+
+    def run_search(self, pool, sims: int) -> None:
+        """All armed simulations of one MCTS.step: at most sims + 1 rounds (root expansion)."""
+        for _ in range(int(sims) + 1):
+            self.search_round(pool)
