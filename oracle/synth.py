@@ -16,8 +16,14 @@ from .games import Game, State
 
 
 def synthetic_state_dict(game: Game, channels: int = 128, num_residual: int = 3,
-                         hidden: int = 128, seed: int = 0) -> Dict[str, torch.Tensor]:
-    """A state_dict with the reference's key names and shapes (SURVEY.md §8 a-N)."""
+                         hidden: int = 128, seed: int = 0, conv_gain: float = 1.6,
+                         fc_scale: float = 2.0) -> Dict[str, torch.Tensor]:
+    """A state_dict with the reference's key names and shapes (SURVEY.md §8 a-N).
+
+    ``conv_gain`` / ``fc_scale`` set the weight standard deviation as gain / sqrt(fan_in).  The
+    defaults (1.6, 2.0) give deliberately sharp policies (used by the golden fixtures and the
+    fp32 tests); (0.577, 0.577) has the spread of a freshly constructed reference net
+    (PyTorch default init, kaiming_uniform(a=sqrt(5)) => std = 1 / sqrt(3 fan_in))."""
     rs = np.random.RandomState(seed)
     g, A, C = game.g, game.num_actions, channels
     sd: Dict[str, torch.Tensor] = {}
@@ -25,7 +31,7 @@ def synthetic_state_dict(game: Game, channels: int = 128, num_residual: int = 3,
     def conv(prefix, cout, cin, k):
         fan_in = cin * k * k
         sd[prefix + ".weight"] = torch.from_numpy(
-            (rs.standard_normal((cout, cin, k, k)) * (1.6 / np.sqrt(fan_in))).astype(np.float32))
+            (rs.standard_normal((cout, cin, k, k)) * (conv_gain / np.sqrt(fan_in))).astype(np.float32))
         sd[prefix + ".bias"] = torch.from_numpy((rs.standard_normal(cout) * 0.1).astype(np.float32))
 
     def bn(prefix, c):
@@ -49,7 +55,7 @@ def synthetic_state_dict(game: Game, channels: int = 128, num_residual: int = 3,
         bn(f"residual_blocks.{i}.bn2", C)
     conv("policy_head.conv1.conv1", C, C, 3)
     bn("policy_head.conv1.bn1", C)
-    linear("policy_head.fc1", A, C * g * g, scale=2.0)
+    linear("policy_head.fc1", A, C * g * g, scale=fc_scale)
     conv("value_head.conv1.conv1", 1, C, 1)
     bn("value_head.conv1.bn1", 1)
     linear("value_head.fc1", hidden, g * g)
