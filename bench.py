@@ -1,0 +1,316 @@
+#!/usr/bin/env python
+"""Headline benchmark: batched MCTS self-play throughput (simulations/s and NN leaf evals/s).
+
+    python bench.py --gpus N --steps K --warmup W [--impl b200|reference] [--workload othello8|hex7]
+
+One "step" = ``num_simulations`` (50) search rounds over the whole pool: every round selects one
+leaf per tree (PUCT descent, terminal leaves handled in place), evaluates the batch with the
+conv policy/value net and expands + backs up.  Workload at N=1: Othello 8x8 self-play, 4096
+concurrent games, ConvolutionalOthelloNet(8) random-init weights, 50 sims/move, cutoff 10,
+Dirichlet alpha 1.0 (BASELINE.json configs[2] at one GPU; --workload hex7 runs configs[1]).
+Games shard across GPUs with no collective on the search path (weak scaling).
+
+Prints ONE JSON line (see the contract in DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOADS = {
+    # name: (game, grid, num_simulations, sample_move_cutoff, dirichlet_alpha, MFLOP per leaf per 3x3 trunk conv)
+    "othello8": ("othello", 8, 50, 10, 1.0),
+    "hex7": ("hex", 7, 50, 10, 0.33),
+}
+METRIC = "mcts_simulations_per_sec"
+UNIT = "sims/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="othello8", choices=sorted(WORKLOADS))
+    ap.add_argument("--trees", type=int, default=4096, help="concurrent games per GPU")
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample per process")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+def workload_config(args):
+    game, grid, sims, cutoff, alpha = WORKLOADS[args.workload]
+    return {"game": game, "grid": grid, "num_simulations": sims, "sample_move_cutoff": cutoff,
+            "dirichlet_alpha": alpha, "dirichlet_factor": 0.25, "weight_seed": 0}
+
+
+def config_block(args, wl, n_gpus):
+    return {
+        "workload": f"{wl['game']} {wl['grid']}x{wl['grid']} self-play MCTS, {args.trees} concurrent games/GPU, "
+                    f"Convolutional{wl['game'].title().replace('_', '')}Net({wl['grid']}) C=128 R=3 random-init, "
+                    f"{wl['num_simulations']} sims/move, cutoff {wl['sample_move_cutoff']}, "
+                    f"dirichlet {wl['dirichlet_alpha']}",
+        "step": f"{wl['num_simulations']} search rounds over the pool (one leaf per tree per round)",
+        "trees_per_gpu": args.trees, "num_simulations": wl["num_simulations"], "parallelism": f"games sharded x{n_gpus}",
+        "l2_policy": "inputs_larger_than_L2 (per-round activations 2x170 MB + GB-scale tree arenas vs 126 MB L2)",
+    }
+
+
+# ------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """Times the oracle port of the reference's CPU self-play (the reference is pure Python and
+    cannot travel to the GPU box) on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_selfplay  # noqa: the one place bench.py may execute oracle/
+    wl = workload_config(args)
+    procs = cpu_selfplay.default_procs()
+    slice_s = 4.0
+    slices = cpu_selfplay.run(wl, procs, args.warmup + args.steps, slice_s)
+    timed = slices[args.warmup:]
+    sims = sum(s[0] for s in timed)
+    evals = sum(s[1] for s in timed)
+    wall = sum(s[2] for s in timed)
+    value = sims / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * wall / max(1, len(timed)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": config_block(args, wl, args.gpus),
+        "leaf_evals_per_sec": evals / wall,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
+                         "sample": f"{procs} processes x 1 torch thread, {len(timed)} slices of {slice_s:.0f} s "
+                                   "of full self-play games (oracle port of the reference loop)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.samples = []
+        self.proc = None
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) >= 6:
+                self.samples.append(parts)
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
+        mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------- b200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py --impl b200 needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200.selfplay import BatchedSelfPlay
+
+    wl = workload_config(args)
+    torch.manual_seed(wl["weight_seed"])
+    if wl["game"] == "othello":
+        from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
+        net = ConvolutionalOthelloNet(wl["grid"])
+    else:
+        from deep_mcts_b200.hex.convolutionalnet import ConvolutionalHexNet
+        net = ConvolutionalHexNet(wl["grid"])
+    net.precision = args.precision
+    net.max_batch = args.trees
+    sims, T = wl["num_simulations"], args.trees
+    engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
+                             replay_capacity=1 << 20, seed=1000 + rank)
+    dn = net.device_net()
+    lib = _lib.load()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also desynchronises the games' phases)
+    for _ in range(args.warmup):
+        engine.run_rounds(sims)
+    barrier()
+    c0 = engine.counters()
+    launches0 = lib.dm_launch_count()
+    dn.profile(True)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        engine.run_rounds(sims)
+    stop.record()
+    barrier()
+    elapsed_ms = start.elapsed_time(stop)
+    clock_info = clocks.stop() if rank == 0 else None
+    prof = dn.profile_read()
+    dn.profile(False)
+    launches = lib.dm_launch_count() - launches0
+    c1 = engine.counters()
+    d = {k: c1[k] - c0[k] for k in c1}
+
+    # ---- end to end through the public batched API with HOST buffers (pinned), fresh roots per step
+    from deep_mcts_b200.pool import TreePool, default_node_capacity
+    p, f, s, fin, _ = engine.pool.states()
+    keep = ~fin
+    idx = np.where(keep)[0]
+    idx = np.resize(idx, T)
+    h_first = torch.from_numpy(f[idx].view(np.int64).copy()).pin_memory()
+    h_second = torch.from_numpy(s[idx].view(np.int64).copy()).pin_memory()
+    h_player = torch.from_numpy(p[idx].copy()).pin_memory()
+    h_visits = torch.empty((T, _lib.DM_MAX_ACTIONS), dtype=torch.int32).pin_memory()
+    h_stats = torch.empty((T, 2), dtype=torch.int32).pin_memory()
+    pool2 = TreePool(net.manager, T, 4096, seed=7)
+    pool2.configure(sims, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, 0, 0.0, 0.25)
+    d_first = torch.empty(T, dtype=torch.int64, device="cuda")
+    d_second = torch.empty(T, dtype=torch.int64, device="cuda")
+    d_player = torch.empty(T, dtype=torch.uint8, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def e2e_step():
+        d_first.copy_(h_first, non_blocking=True)
+        d_second.copy_(h_second, non_blocking=True)
+        d_player.copy_(h_player, non_blocking=True)
+        _lib.call("dm_pool_set_root_state", pool2._h, 0, T, d_first.data_ptr(), d_second.data_ptr(),
+                  d_player.data_ptr(), stream)
+        pool2.begin_step()
+        dn.run_search(pool2, sims)
+        _lib.call("dm_pool_root_visits", pool2._h, pool2._visits.data_ptr(), pool2._stats.data_ptr(), stream)
+        h_visits.copy_(pool2._visits, non_blocking=True)
+        h_stats.copy_(pool2._stats, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    e2e_sims = int(h_stats.sum().item()) * args.e2e_steps  # every step repeats the same work
+    h2d = T * 17
+    d2h = T * (_lib.DM_MAX_ACTIONS * 4 + 8)
+
+    # ---- reduce over ranks: sums of work, max of time
+    vals = torch.tensor([d["simulations"], d["leaf_evals"], e2e_sims, launches], dtype=torch.float64, device="cuda")
+    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    tot_sims, tot_evals, tot_e2e_sims, tot_launches = (float(v) for v in vals.tolist())
+    elapsed_ms, e2e_ms = (float(v) for v in times.tolist())
+
+    if rank == 0:
+        g = wl["grid"]
+        flop_per_leaf_conv = 2.0 * g * g * 9 * 128 * 128  # 18.87 MFLOP at g=8, 14.45 at g=7
+        conv_ms, conv_launches = prof["trunk_conv"]
+        peaks = {}
+        peak_src = "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst)"
+        peak_tflops = 1590.0
+        try:
+            peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+            peak_tflops = float(peaks["bf16_tflops_sustained"])
+            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        except Exception:
+            pass
+        achieved = (d["leaf_evals"] * 7 * flop_per_leaf_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        line = {
+            "metric": METRIC, "value": tot_sims / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": config_block(args, wl, world),
+            "leaf_evals_per_sec": tot_evals / (elapsed_ms * 1e-3),
+            "e2e": {"value": tot_e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h,
+                    "what": "batched MCTS.step through the public API: root states from pinned host memory, "
+                            f"{sims} sims + root expansion per tree, visit counts back to pinned host memory"},
+            "gpu_launches": int(tot_launches),
+            "clocks": clock_info,
+            "roofline": {
+                "kernel": "k_conv3x3_tc (tcgen05 implicit-GEMM 3x3 conv, 7 launches per round)",
+                "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
+                "frac": achieved / peak_tflops if peak_tflops else None, "traffic": None,
+                "peak_source": peak_src, "launches": conv_launches,
+                "avg_launch_ms": conv_ms / conv_launches if conv_launches else None,
+                "algorithmic_flop_per_launch": d["leaf_evals"] * 7 * flop_per_leaf_conv / max(1, conv_launches),
+                "share_of_step": conv_ms / elapsed_ms if elapsed_ms else None,
+            },
+            "kernel_ms": {k: v[0] for k, v in prof.items()},
+            "tree_stats": {"mean_depth": d["depth_sum"] / max(1, d["simulations"]),
+                           "children_scanned_per_sim": d["children_scanned"] / max(1, d["simulations"]),
+                           "terminal_fraction": d["terminal_sims"] / max(1, d["simulations"]),
+                           "games_finished": d["games"], "moves": d["moves"],
+                           "nodes_high_water": c1["nodes_high_water"]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import cpu_selfplay  # noqa: cpu_baseline leg only
+            procs = cpu_selfplay.default_procs()
+            res = cpu_selfplay.run(wl, procs, 1, args.cpu_seconds)
+            cs, ce, cw = res[0]
+            line["cpu_baseline"] = {
+                "value": cs / cw, "unit": UNIT, "cores": procs, "kind": "port",
+                "leaf_evals_per_sec": ce / cw,
+                "sample": f"{procs} processes x 1 torch thread x {args.cpu_seconds:.0f} s of full self-play games "
+                          "with the same net/config (oracle port of the reference loop; the Python reference "
+                          "itself is not present on the GPU box)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -90,6 +90,8 @@ _SIGNATURES = {
     "dm_net_evaluate": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dm_net_forward": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "dm_net_rollout_greedy": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
+    "dm_net_profile": (c_int, [_P, c_int]),
+    "dm_net_profile_read": (c_int, [_P, POINTER(c_double), POINTER(c_int64)]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

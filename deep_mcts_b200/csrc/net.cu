@@ -38,6 +38,13 @@ struct dm_net {
     u8* r_player = nullptr;
     float *r_value = nullptr, *r_probs = nullptr;
     int* r_active = nullptr;
+    // optional CUDA-event timing per kernel class (0 encode+conv1, 1 tcgen05/fp32 trunk conv, 2 heads)
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_events;  // pairs
+    std::vector<int> prof_class;           // class of pair i
+    size_t prof_used = 0;                  // pairs in flight
+    double prof_ms[4] = {0, 0, 0, 0};
+    long long prof_launches[4] = {0, 0, 0, 0};
 };
 
 namespace {
@@ -66,6 +73,40 @@ int net_upload(dm_net* net, T** out, const std::vector<T>& host) {
         int rc__ = (expr);              \
         if (rc__ != DM_OK) return rc__; \
     } while (0)
+
+void prof_fold(dm_net* net) {
+    for (size_t i = 0; i < net->prof_used; ++i) {
+        float ms = 0.f;
+        cudaEventSynchronize(net->prof_events[2 * i + 1]);
+        if (cudaEventElapsedTime(&ms, net->prof_events[2 * i], net->prof_events[2 * i + 1]) == cudaSuccess) {
+            net->prof_ms[net->prof_class[i]] += ms;
+            net->prof_launches[net->prof_class[i]] += 1;
+        }
+    }
+    net->prof_used = 0;
+}
+
+// records the start event of a timed launch; returns the pair index or -1
+int prof_begin(dm_net* net, int cls, cudaStream_t st) {
+    if (!net->prof) return -1;
+    if (net->prof_used * 2 + 2 > net->prof_events.size()) {
+        if (net->prof_events.size() >= 2 * 16384) prof_fold(net);
+        else
+            for (int k = 0; k < 512; ++k) {
+                cudaEvent_t e;
+                cudaEventCreate(&e);
+                net->prof_events.push_back(e);
+            }
+        if (net->prof_class.size() < net->prof_events.size() / 2) net->prof_class.resize(net->prof_events.size() / 2);
+    }
+    int i = (int)net->prof_used++;
+    net->prof_class[i] = cls;
+    cudaEventRecord(net->prof_events[2 * i], st);
+    return i;
+}
+void prof_end(dm_net* net, int i, cudaStream_t st) {
+    if (i >= 0) cudaEventRecord(net->prof_events[2 * i + 1], st);
+}
 
 void free_device(dm_net* net) {
     for (void* p : net->allocations) cudaFree(p);
@@ -118,29 +159,33 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     int enc_blocks = (n + netk::kEncodeBoards - 1) / netk::kEncodeBoards;
     netk::HeadParams hp{net->pfc_b, net->vfc1_w, net->vfc1_b, net->vfc2_w, net->vfc2_b, net->cfg.hidden};
     if (precision == 0) {
+        int pe = prof_begin(net, 0, st);
         netk::k_encode_conv1<false><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player,
                                                                        net->conv1_w, net->conv1_b, C, net->x0, nullptr, 0);
+        prof_end(net, pe, st);
         DM_LAUNCH_CHECK();
         size_t conv_smem = (size_t)gp * gp * C * sizeof(float);
         for (int i = 0; i < R; ++i) {
-            netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x0, net->trunk_w[2 * i],
-                                                           net->trunk_b[2 * i], nullptr, net->x1);
+            { int pc = prof_begin(net, 1, st); netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x0, net->trunk_w[2 * i],
+                                                           net->trunk_b[2 * i], nullptr, net->x1); prof_end(net, pc, st); }
             DM_LAUNCH_CHECK();
-            netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x1, net->trunk_w[2 * i + 1],
-                                                           net->trunk_b[2 * i + 1], net->x0, net->x0);
+            { int pc = prof_begin(net, 1, st); netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x1, net->trunk_w[2 * i + 1],
+                                                           net->trunk_b[2 * i + 1], net->x0, net->x0); prof_end(net, pc, st); }
             DM_LAUNCH_CHECK();
         }
         netk::k_vplane_f32<<<(n * P0 + 127) / 128, 128, 0, st>>>(P0, C, n, count_dev, net->x0, net->vconv_w,
                                                                  net->vconv_b, net->vplane);
         DM_LAUNCH_CHECK();
-        netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x0, net->trunk_w[L - 1],
-                                                       net->trunk_b[L - 1], nullptr, net->x1);
+        { int pc = prof_begin(net, 1, st); netk::k_conv3x3_f32<<<n, 256, conv_smem, st>>>(g.g, C, n, count_dev, net->x0, net->trunk_w[L - 1],
+                                                       net->trunk_b[L - 1], nullptr, net->x1); prof_end(net, pc, st); }
         DM_LAUNCH_CHECK();
         constexpr int kB = 4;
         size_t hs = (size_t)kB * P0 * C * sizeof(float) + (size_t)kB * (net->NA2 + net->cfg.hidden) * sizeof(float);
+        int ph = prof_begin(net, 2, st);
         netk::k_heads<float, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, first, second, player, net->x1,
                                                                     net->pfc_w, C, net->NA2, net->vplane, hp, mode,
                                                                     value_out, probs_out);
+        prof_end(net, ph, st);
         DM_LAUNCH_CHECK();
         return DM_OK;
     }
@@ -148,8 +193,10 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         dm_set_error("bf16 path needs channels == 128 and num_residual >= 1");
         return DM_ERR_INVALID;
     }
+    int pe = prof_begin(net, 0, st);
     netk::k_encode_conv1<true><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player, net->conv1_w,
                                                                   net->conv1_b, C, nullptr, net->a0, net->rows_total);
+    prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
     const size_t conv_smem = netk::conv_smem_bytes(net->geom);
     const int conv_blocks = (int)(((size_t)n * net->geom.P + netk::kRowsPerCta - 1) / netk::kRowsPerCta);
@@ -162,25 +209,39 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     for (int i = 0; i < R; ++i) {
         a.in = net->a0; a.out = net->a1; a.out_nhwc = nullptr; a.residual = nullptr;
         a.w = net->trunk_w16[2 * i]; a.bias = net->trunk_b[2 * i]; a.vhead_w = nullptr; a.vplane = nullptr;
-        netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+        {
+            int pc = prof_begin(net, 1, st);
+            netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+            prof_end(net, pc, st);
+        }
         DM_LAUNCH_CHECK();
         a.in = net->a1; a.out = net->a0; a.residual = net->a0;
         a.w = net->trunk_w16[2 * i + 1]; a.bias = net->trunk_b[2 * i + 1];
         if (i == R - 1) {
             a.vhead_w = net->vconv_w; a.vhead_b = net->vconv_b; a.vplane = net->vplane;
         }
-        netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+        {
+            int pc = prof_begin(net, 1, st);
+            netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+            prof_end(net, pc, st);
+        }
         DM_LAUNCH_CHECK();
     }
     a.in = net->a0; a.out = nullptr; a.out_nhwc = net->t16; a.residual = nullptr;
     a.w = net->trunk_w16[L - 1]; a.bias = net->trunk_b[L - 1]; a.vhead_w = nullptr; a.vplane = nullptr;
-    netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+    {
+        int pc = prof_begin(net, 1, st);
+        netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+        prof_end(net, pc, st);
+    }
     DM_LAUNCH_CHECK();
     constexpr int kB = 8;
     size_t hs = (size_t)kB * P0 * C * sizeof(__nv_bfloat16) + (size_t)kB * (net->NA2 + net->cfg.hidden) * sizeof(float);
+    int ph = prof_begin(net, 2, st);
     netk::k_heads<__nv_bfloat16, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, first, second, player,
                                                                         net->t16, net->pfc_w16, C, net->NA2,
                                                                         net->vplane, hp, mode, value_out, probs_out);
+    prof_end(net, ph, st);
     DM_LAUNCH_CHECK();
     return DM_OK;
 }
@@ -206,6 +267,7 @@ extern "C" int dm_net_destroy(dm_net* net) {
     if (!net) return DM_OK;
     cudaSetDevice(net->cfg.device);
     free_device(net);
+    for (cudaEvent_t e : net->prof_events) cudaEventDestroy(e);
     delete net;
     return DM_OK;
 }
@@ -355,4 +417,28 @@ extern "C" int dm_net_rollout_greedy(dm_net* net, int precision, int n, const ui
     }
     dm_set_error("dm_net_rollout_greedy: games did not finish");
     return DM_ERR_STATE;
+}
+
+extern "C" int dm_net_profile(dm_net* net, int enable) {
+    DM_CHECK_ARG(net, "dm_net_profile: null net");
+    DM_CUDA(cudaSetDevice(net->cfg.device));
+    prof_fold(net);
+    net->prof = enable != 0;
+    if (enable)
+        for (int k = 0; k < 4; ++k) {
+            net->prof_ms[k] = 0;
+            net->prof_launches[k] = 0;
+        }
+    return DM_OK;
+}
+
+extern "C" int dm_net_profile_read(dm_net* net, double ms_out[4], int64_t launches_out[4]) {
+    DM_CHECK_ARG(net && ms_out && launches_out, "dm_net_profile_read: null argument");
+    DM_CUDA(cudaSetDevice(net->cfg.device));
+    prof_fold(net);
+    for (int k = 0; k < 4; ++k) {
+        ms_out[k] = net->prof_ms[k];
+        launches_out[k] = net->prof_launches[k];
+    }
+    return DM_OK;
 }

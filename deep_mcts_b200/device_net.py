@@ -120,6 +120,17 @@ class DeviceNet:
                       s.data_ptr(), p.data_ptr(), out.data_ptr(), current_stream())
         return out.cpu().numpy()
 
+    # ------------------------------------------------------------------------- profiling
+    def profile(self, enable: bool) -> None:
+        _lib.call("dm_net_profile", self._h, 1 if enable else 0)
+
+    def profile_read(self) -> dict:
+        """{class: (milliseconds, launches)} for 'encode', 'trunk_conv', 'heads' since profile(True)."""
+        ms = (_lib.c_double * 4)()
+        launches = (_lib.c_int64 * 4)()
+        _lib.call("dm_net_profile_read", self._h, ms, launches)
+        return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(("encode", "trunk_conv", "heads"))}
+
     # --------------------------------------------------------------------------- search
     def search_round(self, pool, selfplay: bool = False) -> None:
         """One select -> evaluate -> expand/backup round for every tree of the pool (no host sync)."""

@@ -226,6 +226,12 @@ int dm_net_forward(dm_net* net, int precision, int n, const uint64_t* first_dev,
 int dm_net_rollout_greedy(dm_net* net, int precision, int n, const uint64_t* first_dev,
                           const uint64_t* second_dev, const uint8_t* player_dev, float* outcome_dev,
                           void* stream);
+/* CUDA-event timing of the network kernels on their launch stream, per kernel class:
+ * [0] encode + first conv, [1] trunk 3x3 convs (the tcgen05 kernel at precision 1), [2] heads.
+ * dm_net_profile(net, 1) clears and starts, dm_net_profile_read synchronises and returns the
+ * accumulated milliseconds and launch counts.  Used by bench.py for the roofline. */
+int dm_net_profile(dm_net* net, int enable);
+int dm_net_profile_read(dm_net* net, double ms_out[4], int64_t launches_out[4]);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t dm_launch_count(void);
 
