@@ -29,7 +29,9 @@ struct dm_net {
     float vconv_b = 0.f, vfc2_b = 0.f;
     // bf16 weights
     std::vector<__nv_bfloat16*> trunk_w16;
-    __nv_bfloat16* pfc_w16 = nullptr;
+    __nv_bfloat16* pfc_w16 = nullptr;  // [g*g*16][NA][8] (k_policy_fc_tc B operand)
+    int fc_na = 0, fc_split = 1;
+    float* fc_partial = nullptr;       // [split][max_batch rounded to 128][NA]
     // activations
     float *x0 = nullptr, *x1 = nullptr, *vplane = nullptr;
     __nv_bfloat16 *a0 = nullptr, *a1 = nullptr, *t16 = nullptr;
@@ -227,7 +229,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         }
         DM_LAUNCH_CHECK();
     }
-    a.in = net->a0; a.out = nullptr; a.out_nhwc = net->t16; a.residual = nullptr;
+    a.in = net->a0; a.out = nullptr; a.out_nhwc = nullptr; a.out_fc = net->t16; a.residual = nullptr;
     a.w = net->trunk_w16[L - 1]; a.bias = net->trunk_b[L - 1]; a.vhead_w = nullptr; a.vplane = nullptr;
     {
         int pc = prof_begin(net, 1, st);
@@ -235,12 +237,14 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         prof_end(net, pc, st);
     }
     DM_LAUNCH_CHECK();
-    constexpr int kB = 8;
-    size_t hs = (size_t)kB * P0 * C * sizeof(__nv_bfloat16) + (size_t)kB * (net->NA2 + net->cfg.hidden) * sizeof(float);
+    const int n_cap = (net->cfg.max_batch + 127) / 128 * 128;
+    netk::FcArgs fa{net->t16, net->pfc_w16, net->fc_partial, P0, net->fc_na, net->fc_split, n, n_cap, count_dev};
     int ph = prof_begin(net, 2, st);
-    netk::k_heads<__nv_bfloat16, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, first, second, player,
-                                                                        net->t16, net->pfc_w16, C, net->NA2,
-                                                                        net->vplane, hp, mode, value_out, probs_out);
+    netk::k_policy_fc_tc<<<dim3((n + 127) / 128, net->fc_split), netk::kFcThreads, netk::fc_smem_bytes(net->fc_na), st>>>(fa);
+    ++g_dm_launches;
+    netk::k_heads_finish<<<(n + 3) / 4, 128, 0, st>>>(g, n, count_dev, first, second, player, net->fc_partial,
+                                                     net->fc_split, n_cap, net->fc_na, net->vplane, hp, mode,
+                                                     value_out, probs_out);
     prof_end(net, ph, st);
     DM_LAUNCH_CHECK();
     return DM_OK;
@@ -329,20 +333,29 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
             pack_trunk_bf16(hw.trunk_w[l], C, packed);
             DM_TRY(net_upload(net, &net->trunk_w16[l], packed));
         }
-        std::vector<__nv_bfloat16> p16(hw.pfc_w.size());
-        for (size_t i = 0; i < p16.size(); ++i) p16[i] = __float2bfloat16(hw.pfc_w[i]);
+        // policy FC weights as the tcgen05 B operand: [(pos*16 + kc)][a][8 channels]
+        net->fc_na = netk::fc_padded_actions(A);
+        net->fc_split = netk::fc_split(g);
+        std::vector<__nv_bfloat16> p16((size_t)P0 * 16 * net->fc_na * 8, __float2bfloat16(0.f));
+        for (int pos = 0; pos < P0; ++pos)
+            for (int c = 0; c < C; ++c)
+                for (int a = 0; a < A; ++a)
+                    p16[(((size_t)pos * 16 + c / 8) * net->fc_na + a) * 8 + (c % 8)] =
+                        __float2bfloat16(hw.pfc_w[((size_t)pos * C + c) * hw.NA2 + a]);
         DM_TRY(net_upload(net, &net->pfc_w16, p16));
         net->rows_total = netk::conv_rows_total(net->geom, n);
         size_t abytes = (size_t)netk::kChunks * net->rows_total * 16;
         // zeroed once: pad rows are never written afterwards and must stay zero
         DM_TRY(net_alloc_bytes(net, (void**)&net->a0, abytes, true));
         DM_TRY(net_alloc_bytes(net, (void**)&net->a1, abytes, true));
-        DM_TRY(net_alloc_bytes(net, (void**)&net->t16, act * sizeof(__nv_bfloat16), true));
+        size_t n128 = ((size_t)n + 127) / 128 * 128;
+        DM_TRY(net_alloc_bytes(net, (void**)&net->t16, n128 * P0 * C * sizeof(__nv_bfloat16), true));
+        DM_TRY(net_alloc_bytes(net, (void**)&net->fc_partial, (size_t)net->fc_split * n128 * net->fc_na * sizeof(float),
+                               true));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv_smem_bytes(net->geom)));
-        size_t hs = (size_t)8 * P0 * C * sizeof(__nv_bfloat16) + (size_t)8 * (hw.NA2 + H) * sizeof(float);
-        DM_CUDA(cudaFuncSetAttribute(netk::k_heads<__nv_bfloat16, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)hs));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_policy_fc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::fc_smem_bytes(net->fc_na)));
         net->bf16_ready = true;
     }
     {

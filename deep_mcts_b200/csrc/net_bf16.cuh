@@ -35,7 +35,8 @@ constexpr int kConvThreads = 192;
 struct ConvArgs {
     const __nv_bfloat16* in;        // chunked rows
     __nv_bfloat16* out;             // chunked rows, or null
-    __nv_bfloat16* out_nhwc;        // dense [board][pos][128] (policy conv), or null
+    __nv_bfloat16* out_nhwc;        // dense [board][pos][128], or null
+    __nv_bfloat16* out_fc;          // policy-FC A-operand layout (see k_policy_fc_tc), or null
     const __nv_bfloat16* residual;  // chunked rows, or null (may alias out)
     const __nv_bfloat16* w;         // [9][16][128][8]
     const float* bias;              // [128]
@@ -264,6 +265,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
                         *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
                     if (args.out_nhwc)
                         *reinterpret_cast<uint4*>(args.out_nhwc + ((size_t)b * P0 + y * g + x) * kC + cc * 32 + c4 * 8) = o;
+                    if (args.out_fc)
+                        *reinterpret_cast<uint4*>(args.out_fc +
+                                                  ((((size_t)(b >> 7) * P0 + (y * g + x)) * kChunks + (cc * 4 + c4)) * 128 +
+                                                   (b & 127)) * 8) = o;
                 }
             }
             if (valid && args.vhead_w) args.vplane[(size_t)b * P0 + y * g + x] = fmaxf(vacc + args.vhead_b, 0.f);
@@ -274,6 +279,219 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
+}
+
+
+
+// ============================================================================================
+// Policy-head fully connected layer on tcgen05 (reference convolutionalnet.py:146-153):
+//   logits[b][a] = sum_{pos, c} T[b][pos][c] * W[a][c*g*g + pos]
+// as a split-K GEMM: M = 128 boards per tile, N = NA (actions padded to a multiple of 16),
+// K = g*g*128 cut by board position: one pipeline stage = one position = 16 channel chunks.
+//   A: policy-conv output written by k_conv3x3_tc in the layout
+//        t_fc[((tile * g*g + pos) * 16 + kc) * 128 + board_in_tile][8]        (32 KB per stage)
+//   B: fc_w[(pos * 16 + kc) * NA + a][8]                                      (NA * 256 B per stage)
+//   D: 128 lanes x NA fp32 columns in TMEM -> partial[split][board][NA]
+// Partials are summed in a fixed order by k_heads_finish, so results are deterministic.
+constexpr int kFcThreads = 192;
+constexpr int kFcStages = 4;
+constexpr int kFcStageA = 128 * kC * 2;  // 32 KB
+
+inline int fc_padded_actions(int A) { return (A + 15) / 16 * 16; }
+inline int fc_split(int g) {
+    int P0 = g * g;
+    for (int s = 8; s >= 1; --s)
+        if (P0 % s == 0) return s;
+    return 1;
+}
+inline size_t fc_smem_bytes(int NA) { return 1024 + (size_t)kFcStages * (kFcStageA + (size_t)NA * 256) + 256; }
+
+struct FcArgs {
+    const __nv_bfloat16* t_fc;
+    const __nv_bfloat16* w;  // [g*g*16][NA][8]
+    float* partial;          // [split][n_boards_cap][NA]
+    int P0, NA, split, n_boards, n_boards_cap;
+    const int* count_dev;
+};
+
+__global__ void __launch_bounds__(kFcThreads, 1) k_policy_fc_tc(FcArgs args) {
+    extern __shared__ unsigned char smem_raw[];
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const int live = live_count(args.count_dev, args.n_boards);
+    if (tile * 128 >= live) return;
+    const int NA = args.NA;
+    const u32 stage_b_bytes = (u32)NA * 256;
+    unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
+    unsigned char* s_a = base;                                  // [stages][32 KB]
+    unsigned char* s_b = s_a + (size_t)kFcStages * kFcStageA;   // [stages][NA*256]
+    u64* s_bar = (u64*)(s_b + (size_t)kFcStages * stage_b_bytes);  // full[4], empty[4], acc
+    u32* s_tmem = (u32*)(s_bar + 2 * kFcStages + 1);
+    const u32 bar_full0 = smem_u32(&s_bar[0]), bar_empty0 = smem_u32(&s_bar[kFcStages]);
+    const u32 bar_acc = smem_u32(&s_bar[2 * kFcStages]);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kFcStages; ++s) {
+            mbar_init(bar_full0 + 8 * s, 1);
+            mbar_init(bar_empty0 + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(128)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = *s_tmem;
+    const int pos_per_split = args.P0 / args.split;
+    const int pos0 = split * pos_per_split;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int i = 0; i < pos_per_split; ++i) {
+                int st = i % kFcStages;
+                if (i >= kFcStages) mbar_wait(bar_empty0 + 8 * st, ((i / kFcStages) - 1) & 1);
+                mbar_expect_tx(bar_full0 + 8 * st, kFcStageA + stage_b_bytes);
+                int pos = pos0 + i;
+                bulk_g2s(smem_u32(s_a + (size_t)st * kFcStageA),
+                         args.t_fc + ((size_t)tile * args.P0 + pos) * (size_t)(16 * 128 * 8), kFcStageA,
+                         bar_full0 + 8 * st);
+                bulk_g2s(smem_u32(s_b + (size_t)st * stage_b_bytes), args.w + (size_t)pos * 16 * NA * 8, stage_b_bytes,
+                         bar_full0 + 8 * st);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const u32 idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(NA >> 3) << 17) | ((u32)(128 >> 4) << 24);
+            const u32 lbo_a = 128 * 16, lbo_b = (u32)NA * 16, sbo = 128;
+            for (int i = 0; i < pos_per_split; ++i) {
+                int st = i % kFcStages;
+                mbar_wait(bar_full0 + 8 * st, (i / kFcStages) & 1);
+                tc_fence_after();
+                const u32 a_addr = smem_u32(s_a + (size_t)st * kFcStageA);
+                const u32 b_addr = smem_u32(s_b + (size_t)st * stage_b_bytes);
+#pragma unroll
+                for (int k16 = 0; k16 < 8; ++k16) {
+                    u64 ad = umma_desc(a_addr + (u32)(2 * k16) * lbo_a, lbo_a, sbo);
+                    u64 bd = umma_desc(b_addr + (u32)(2 * k16) * lbo_b, lbo_b, sbo);
+                    tc_mma_bf16(tmem_base, ad, bd, idesc, (i | k16) ? 1u : 0u);
+                }
+                tc_commit(bar_empty0 + 8 * st);
+            }
+            tc_commit(bar_acc);
+        }
+    } else {
+        const int quarter = warp & 3;
+        mbar_wait(bar_acc, 0);
+        tc_fence_after();
+        const int board = tile * 128 + quarter * 32 + lane;
+        float* out = args.partial + ((size_t)split * args.n_boards_cap + board) * NA;
+        for (int c0 = 0; c0 < NA; c0 += 16) {
+            u32 v[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(tmem_base + ((u32)(quarter * 32) << 16) + (u32)c0)
+                : "memory");
+            tc_wait_ld();
+            if (board < live) {
+#pragma unroll
+                for (int j = 0; j < 16; j += 4) {
+                    float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                           __uint_as_float(v[j + 3]));
+                    *reinterpret_cast<float4*>(out + c0 + j) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
+// Sums the split-K partial logits, runs the value-head FCs and GameNet.evaluate's
+// post-processing (gamenet.py:67-85).  One warp per board.
+__global__ void __launch_bounds__(128) k_heads_finish(GameCfg cfg, int n, const int* count_dev, const u64* first,
+                                                      const u64* second, const u8* player,
+                                                      const float* __restrict__ partial, int split, int n_cap, int NA,
+                                                      const float* __restrict__ vplane, HeadParams hp, int mode,
+                                                      float* value_out, float* probs_out) {
+    __shared__ float s_vp[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gb = blockIdx.x * 4 + warp;
+    if (gb >= live_count(count_dev, n)) return;
+    const int P0 = cfg.g * cfg.g, A = cfg.num_actions;
+    GState s;
+    s.first = first[gb];
+    s.second = second[gb];
+    s.player = player[gb];
+    for (int p = lane; p < P0; p += 32) s_vp[warp][p] = vplane[(size_t)gb * P0 + p];
+    __syncwarp();
+    float v = 0.f;
+    for (int j = lane; j < hp.H; j += 32) {
+        const float* wr = hp.vfc1_w + (size_t)j * P0;
+        float acc = hp.vfc1_b[j];
+        for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], wr[p], acc);
+        v = fmaf(fmaxf(acc, 0.f), hp.vfc2_w[j], v);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(DM_FULL_MASK, v, off);
+    v += hp.vfc2_b;
+    const bool transpose = (cfg.game == DM_HEX || cfg.game == DM_HEX_SWAP) && s.player == 0;
+    float lg[3];
+    int na = 0;
+    for (int a = lane; a < A; a += 32, ++na) {
+        int src = a;
+        if (transpose && a < P0) src = (a % cfg.g) * cfg.g + a / cfg.g;
+        float acc = 0.f;
+        for (int sp = 0; sp < split; ++sp) acc += partial[((size_t)sp * n_cap + gb) * NA + src];
+        lg[na] = acc + hp.pfc_b[src];
+    }
+    if (mode == 1) {
+        if (lane == 0) value_out[gb] = v;
+        na = 0;
+        for (int a = lane; a < DM_MAX_ACTIONS; a += 32, ++na)
+            probs_out[(size_t)gb * DM_MAX_ACTIONS + a] = a < A ? lg[na] : 0.f;
+        return;
+    }
+    float tv = tanhf(v);
+    if (s.player == 1) tv = -tv;
+    if (lane == 0) value_out[gb] = (tv + 1.f) / 2.f;
+    float mx = -INFINITY;
+    na = 0;
+    for (int a = lane; a < A; a += 32, ++na) mx = fmaxf(mx, lg[na]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(DM_FULL_MASK, mx, off));
+    float e[3], sum = 0.f;
+    na = 0;
+    for (int a = lane; a < A; a += 32, ++na) {
+        e[na] = expf(lg[na] - mx);
+        sum += e[na];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(DM_FULL_MASK, sum, off);
+    bool extra;
+    u64 mask = game_legal_mask(cfg, s, extra);
+    float msum = 0.f;
+    na = 0;
+    for (int a = lane; a < A; a += 32, ++na) {
+        bool legal = (a == cfg.cells) ? extra : (bool)((mask >> a) & 1);
+        e[na] = legal ? e[na] / sum : 0.f;
+        msum += e[na];
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) msum += __shfl_xor_sync(DM_FULL_MASK, msum, off);
+    na = 0;
+    for (int a = lane; a < DM_MAX_ACTIONS; a += 32, ++na)
+        probs_out[(size_t)gb * DM_MAX_ACTIONS + a] = a < A ? e[na] / msum : 0.f;
 }
 
 }  // namespace netk

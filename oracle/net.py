@@ -83,8 +83,8 @@ def forward(game: Game, sd: Dict[str, torch.Tensor], planes: torch.Tensor) -> Tu
         g = game.g
         second = planes[:, 2, 0, 0] == 0
         logits = logits.clone()
-        board = logits[:, : g * g].reshape(-1, g, g)
-        board[second] = board[second].transpose(1, 2)
+        board = logits[:, : g * g].reshape(-1, g, g).clone()
+        board[second] = board[second].transpose(1, 2).clone()
         logits[:, : g * g] = board.reshape(-1, g * g)
     return v, logits
 
