@@ -2,6 +2,8 @@
 // deep_mcts/convolutionalnet.py:22-170 behind GameNet.evaluate / forward, gamenet.py:61-128).
 // precision 0 = fp32 CUDA cores (any architecture the reference can build),
 // precision 1 = bf16 tcgen05 trunk (channels == 128, num_residual >= 1).
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <new>
@@ -31,6 +33,8 @@ struct dm_net {
     std::vector<__nv_bfloat16*> trunk_w16;
     __nv_bfloat16* pfc_w16 = nullptr;  // [g*g*16][NA][8] (k_policy_fc_tc B operand)
     int fc_na = 0, fc_split = 1;
+    bool conv_v1 = false;  // DM_CONV_V1=1 selects the non-persistent trunk kernel (A/B testing)
+    int sm_count = 148;
     float* fc_partial = nullptr;       // [split][max_batch rounded to 128][NA]
     // activations
     float *x0 = nullptr, *x1 = nullptr, *vplane = nullptr;
@@ -200,8 +204,13 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
                                                                   net->conv1_b, C, nullptr, net->a0, net->rows_total);
     prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
-    const size_t conv_smem = netk::conv_smem_bytes(net->geom);
-    const int conv_blocks = (int)(((size_t)n * net->geom.P + netk::kRowsPerCta - 1) / netk::kRowsPerCta);
+    const bool v1 = net->conv_v1;
+    const size_t conv_smem = v1 ? netk::conv_smem_bytes(net->geom) : netk::conv2_smem_bytes(net->geom);
+    const int conv_items = (int)(((size_t)n * net->geom.P + netk::kItemRows - 1) / netk::kItemRows);
+    const int conv_blocks = v1 ? (int)(((size_t)n * net->geom.P + netk::kRowsPerCta - 1) / netk::kRowsPerCta)
+                               : (conv_items < net->sm_count ? conv_items : net->sm_count);
+    const int conv_threads = v1 ? netk::kConvThreads : netk::kConv2Threads;
+    auto conv_kernel = v1 ? netk::k_conv3x3_tc : netk::k_conv3x3_tc2;
     netk::ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.rows_total = net->rows_total;
@@ -213,7 +222,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         a.w = net->trunk_w16[2 * i]; a.bias = net->trunk_b[2 * i]; a.vhead_w = nullptr; a.vplane = nullptr;
         {
             int pc = prof_begin(net, 1, st);
-            netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+            conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
             prof_end(net, pc, st);
         }
         DM_LAUNCH_CHECK();
@@ -224,7 +233,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         }
         {
             int pc = prof_begin(net, 1, st);
-            netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+            conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
             prof_end(net, pc, st);
         }
         DM_LAUNCH_CHECK();
@@ -233,7 +242,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     a.w = net->trunk_w16[L - 1]; a.bias = net->trunk_b[L - 1]; a.vhead_w = nullptr; a.vplane = nullptr;
     {
         int pc = prof_begin(net, 1, st);
-        netk::k_conv3x3_tc<<<conv_blocks, netk::kConvThreads, conv_smem, st>>>(a);
+        conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
         prof_end(net, pc, st);
     }
     DM_LAUNCH_CHECK();
@@ -343,7 +352,12 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                     p16[(((size_t)pos * 16 + c / 8) * net->fc_na + a) * 8 + (c % 8)] =
                         __float2bfloat16(hw.pfc_w[((size_t)pos * C + c) * hw.NA2 + a]);
         DM_TRY(net_upload(net, &net->pfc_w16, p16));
-        net->rows_total = netk::conv_rows_total(net->geom, n);
+        {
+            const char* env = getenv("DM_CONV_V1");
+            net->conv_v1 = env && env[0] == '1';
+            cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, net->cfg.device);
+        }
+        net->rows_total = std::max(netk::conv_rows_total(net->geom, n), netk::conv2_rows_total(net->geom, n));
         size_t abytes = (size_t)netk::kChunks * net->rows_total * 16;
         // zeroed once: pad rows are never written afterwards and must stay zero
         DM_TRY(net_alloc_bytes(net, (void**)&net->a0, abytes, true));
@@ -354,6 +368,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                true));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv_smem_bytes(net->geom)));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::conv2_smem_bytes(net->geom)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_policy_fc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::fc_smem_bytes(net->fc_na)));
         net->bf16_ready = true;

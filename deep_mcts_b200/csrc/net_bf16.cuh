@@ -284,6 +284,236 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
 
 
 // ============================================================================================
+// Persistent variant of the trunk convolution (the one the engine runs): one CTA per SM loops
+// over work items of 256 rows (two 128-row tiles).  Activation tiles and TMEM accumulators are
+// double buffered, so while the epilogue warps drain item j the tensor core already works on
+// item j+1 and the producers fetch item j+2:
+//   warp 0  weight producer  (9 taps x 32 KB per item through kStages2 stages)
+//   warp 1  TMEM allocator + MMA issuer (2 tiles x 9 taps x 8 k-steps = 144 tcgen05.mma per item)
+//   warp 2  activation producer (16 chunk copies per item into A buffer j & 1)
+//   warps 3-6 epilogue (TMEM lane quarter = warp % 4); residual rows are prefetched into
+//           registers before the accumulator is awaited
+// TMEM: accumulator (buf, tile) at column (buf*2 + tile) * 128.
+constexpr int kItemTiles = 2;
+constexpr int kItemRows = kTileM * kItemTiles;  // 256
+constexpr int kStages2 = 2;
+constexpr int kConv2Threads = 224;
+
+__host__ __device__ inline int conv2_a_rows(const RowGeom& geom) { return kItemRows + 2 * geom.halo; }
+inline size_t conv2_smem_bytes(const RowGeom& geom) {
+    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStageBytes + 2 * kC * sizeof(float) +
+           256;
+}
+inline size_t conv2_rows_total(const RowGeom& geom, int n_boards) {
+    size_t body = ((size_t)n_boards * geom.P + kItemRows - 1) / kItemRows * kItemRows;
+    return body + 2 * (size_t)geom.halo;
+}
+
+__device__ __forceinline__ void mbar_arrive(u32 bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args) {
+    extern __shared__ unsigned char smem_raw[];
+    const RowGeom geom = args.geom;
+    const int a_rows = conv2_a_rows(geom);
+    const int live = live_count(args.count_dev, args.n_boards);
+    const int n_items = (int)(((size_t)live * geom.P + kItemRows - 1) / kItemRows);
+    if ((int)blockIdx.x >= n_items) return;
+
+    unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
+    const u32 a_buf_bytes = (u32)kChunks * a_rows * 16;
+    unsigned char* s_a = base;                                  // [2][16][a_rows][16 B]
+    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][32 KB]
+    float* s_bias = (float*)(s_b + (size_t)kStages2 * kStageBytes);
+    float* s_vw = s_bias + kC;
+    u64* s_bar = (u64*)(s_vw + kC);
+    // barriers: b_full[S], b_empty[S], a_full[2], a_empty[2], acc_full[2], acc_empty[2]
+    const u32 bar_bfull = smem_u32(&s_bar[0]), bar_bempty = smem_u32(&s_bar[kStages2]);
+    const u32 bar_afull = smem_u32(&s_bar[2 * kStages2]), bar_aempty = smem_u32(&s_bar[2 * kStages2 + 2]);
+    const u32 bar_accfull = smem_u32(&s_bar[2 * kStages2 + 4]), bar_accempty = smem_u32(&s_bar[2 * kStages2 + 6]);
+    u32* s_tmem = (u32*)(s_bar + 2 * kStages2 + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kC; i += blockDim.x) {
+        s_bias[i] = args.bias[i];
+        s_vw[i] = args.vhead_w ? args.vhead_w[i] : 0.f;
+    }
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_afull + 8 * b, 1);
+            mbar_init(bar_aempty + 8 * b, 1);
+            mbar_init(bar_accfull + 8 * b, 1);
+            mbar_init(bar_accempty + 8 * b, 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ---- weight producer
+            int s = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+                for (int tap = 0; tap < 9; ++tap, ++s) {
+                    int st = s % kStages2;
+                    if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
+                    mbar_expect_tx(bar_bfull + 8 * st, kStageBytes);
+                    bulk_g2s(smem_u32(s_b + (size_t)st * kStageBytes), args.w + (size_t)tap * kC * kC, kStageBytes,
+                             bar_bfull + 8 * st);
+                }
+            }
+        }
+    } else if (warp == 2) {
+        if (lane == 0) {
+            // ---- activation producer
+            const u32 a_chunk_bytes = (u32)a_rows * 16;
+            int j = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+                int buf = j & 1;
+                if (j >= 2) mbar_wait(bar_aempty + 8 * buf, ((j >> 1) - 1) & 1);
+                mbar_expect_tx(bar_afull + 8 * buf, a_chunk_bytes * kChunks);
+                const size_t row0 = (size_t)it * kItemRows;
+                for (int kc = 0; kc < kChunks; ++kc)
+                    bulk_g2s(smem_u32(s_a + (size_t)buf * a_buf_bytes + (size_t)kc * a_chunk_bytes),
+                             args.in + ((size_t)kc * args.rows_total + row0) * 8, a_chunk_bytes, bar_afull + 8 * buf);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ---- MMA issuer
+            const u32 lbo_a = (u32)a_rows * 16, lbo_b = kC * 16, sbo = 128;
+            int j = 0, s = 0;
+            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+                int buf = j & 1;
+                mbar_wait(bar_afull + 8 * buf, (j >> 1) & 1);
+                if (j >= 2) mbar_wait(bar_accempty + 8 * buf, ((j >> 1) - 1) & 1);
+                tc_fence_after();
+                const u32 a_base = smem_u32(s_a + (size_t)buf * a_buf_bytes);
+                for (int tap = 0; tap < 9; ++tap, ++s) {
+                    int st = s % kStages2;
+                    mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
+                    tc_fence_after();
+                    const int shift = (tap / 3 - 1) * geom.Wp + (tap % 3 - 1);
+                    const u32 b_addr = smem_u32(s_b + (size_t)st * kStageBytes);
+#pragma unroll
+                    for (int tile = 0; tile < kItemTiles; ++tile) {
+                        const u32 a_addr = a_base + (u32)(geom.halo + tile * kTileM + shift) * 16;
+#pragma unroll
+                        for (int k16 = 0; k16 < kC / 16; ++k16) {
+                            u64 ad = umma_desc(a_addr + (u32)(2 * k16) * lbo_a, lbo_a, sbo);
+                            u64 bd = umma_desc(b_addr + (u32)(2 * k16) * lbo_b, lbo_b, sbo);
+                            tc_mma_bf16(tmem_base + (u32)((buf * kItemTiles + tile) * kC), ad, bd, kIdescBf16,
+                                        (tap | k16) ? 1u : 0u);
+                        }
+                    }
+                    tc_commit(bar_bempty + 8 * st);
+                }
+                tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
+                tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled
+            }
+        }
+    } else {
+        // ---- epilogue warps 3..6
+        const int quarter = warp & 3;
+        const int g = geom.g, P0 = g * g;
+        int j = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            const int buf = j & 1;
+            bool waited = false;
+            for (int tile = 0; tile < kItemTiles; ++tile) {
+                const size_t q = (size_t)it * kItemRows + (size_t)tile * kTileM + quarter * 32 + lane;
+                const size_t m = q + geom.halo;
+                const int b = (int)(q / geom.P), rem = (int)(q % geom.P);
+                const int y = rem / geom.Wp, x = rem % geom.Wp;
+                const bool valid = (b < live) && (y < g) && (x < g);
+                // prefetch this row's residual (all 128 channels) before waiting for the tensor core
+                uint4 res[kChunks];
+                if (args.residual && valid) {
+#pragma unroll
+                    for (int kc = 0; kc < kChunks; ++kc)
+                        res[kc] = *reinterpret_cast<const uint4*>(args.residual + ((size_t)kc * args.rows_total + m) * 8);
+                }
+                if (!waited) {
+                    mbar_wait(bar_accfull + 8 * buf, (j >> 1) & 1);
+                    tc_fence_after();
+                    waited = true;
+                }
+                float vacc = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < kC / 32; ++cc) {
+                    u32 v[32];
+                    tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)((buf * kItemTiles + tile) * kC + cc * 32), v);
+                    tc_wait_ld();
+                    if (valid) {
+                        float f[32];
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(v[jj]) + s_bias[cc * 32 + jj];
+                        if (args.residual) {
+#pragma unroll
+                            for (int c4 = 0; c4 < 4; ++c4) {
+                                const uint4 r = res[cc * 4 + c4];
+                                const u32 rw[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                                for (int jj = 0; jj < 4; ++jj) {
+                                    f[c4 * 8 + 2 * jj] += __uint_as_float(rw[jj] << 16);
+                                    f[c4 * 8 + 2 * jj + 1] += __uint_as_float(rw[jj] & 0xffff0000u);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int jj = 0; jj < 32; ++jj) {
+                            f[jj] = fmaxf(f[jj], 0.f);
+                            vacc = fmaf(f[jj], s_vw[cc * 32 + jj], vacc);
+                        }
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            uint4 o;
+                            o.x = pack_bf16(f[c4 * 8 + 0], f[c4 * 8 + 1]);
+                            o.y = pack_bf16(f[c4 * 8 + 2], f[c4 * 8 + 3]);
+                            o.z = pack_bf16(f[c4 * 8 + 4], f[c4 * 8 + 5]);
+                            o.w = pack_bf16(f[c4 * 8 + 6], f[c4 * 8 + 7]);
+                            if (args.out)
+                                *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
+                            if (args.out_nhwc)
+                                *reinterpret_cast<uint4*>(args.out_nhwc + ((size_t)b * P0 + y * g + x) * kC + cc * 32 +
+                                                          c4 * 8) = o;
+                            if (args.out_fc)
+                                *reinterpret_cast<uint4*>(
+                                    args.out_fc +
+                                    ((((size_t)(b >> 7) * P0 + (y * g + x)) * kChunks + (cc * 4 + c4)) * 128 + (b & 127)) * 8) = o;
+                        }
+                    }
+                }
+                if (valid && args.vhead_w) args.vplane[(size_t)b * P0 + y * g + x] = fmaxf(vacc + args.vhead_b, 0.f);
+            }
+            // this warp is done reading accumulator `buf`
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_accempty + 8 * buf);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ============================================================================================
 // Policy-head fully connected layer on tcgen05 (reference convolutionalnet.py:146-153):
 //   logits[b][a] = sum_{pos, c} T[b][pos][c] * W[a][c*g*g + pos]
 // as a split-K GEMM: M = 128 boards per tile, N = NA (actions padded to a multiple of 16),
