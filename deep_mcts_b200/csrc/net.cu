@@ -27,7 +27,7 @@ struct dm_net {
     // fp32 weights
     float *conv1_w = nullptr, *conv1_b = nullptr;
     std::vector<float*> trunk_w, trunk_b;
-    float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
+    float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_t = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
     float vconv_b = 0.f, vfc2_b = 0.f;
     // bf16 weights
     std::vector<__nv_bfloat16*> trunk_w16;
@@ -163,7 +163,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     const int L = 2 * R + 1;
     size_t enc_smem = (size_t)(27 * C + C + netk::kEncodeBoards * 3 * gp * gp) * sizeof(float);
     int enc_blocks = (n + netk::kEncodeBoards - 1) / netk::kEncodeBoards;
-    netk::HeadParams hp{net->pfc_b, net->vfc1_w, net->vfc1_b, net->vfc2_w, net->vfc2_b, net->cfg.hidden};
+    netk::HeadParams hp{net->pfc_b, net->vfc1_w, net->vfc1_t, net->vfc1_b, net->vfc2_w, net->vfc2_b, net->cfg.hidden};
     if (precision == 0) {
         int pe = prof_begin(net, 0, st);
         netk::k_encode_conv1<false><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player,
@@ -319,6 +319,12 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
     DM_TRY(net_upload(net, &net->vconv_w, hw.vconv_w));
     net->vconv_b = hw.vconv_b;
     DM_TRY(net_upload(net, &net->vfc1_w, hw.vfc1_w));
+    {
+        std::vector<float> t((size_t)P0 * H);
+        for (int j = 0; j < H; ++j)
+            for (int p = 0; p < P0; ++p) t[(size_t)p * H + j] = hw.vfc1_w[(size_t)j * P0 + p];
+        DM_TRY(net_upload(net, &net->vfc1_t, t));
+    }
     DM_TRY(net_upload(net, &net->vfc1_b, hw.vfc1_b));
     DM_TRY(net_upload(net, &net->vfc2_w, hw.vfc2_w));
     net->vfc2_b = hw.vfc2_b;

@@ -667,9 +667,9 @@ __global__ void __launch_bounds__(128) k_heads_finish(GameCfg cfg, int n, const 
     __syncwarp();
     float v = 0.f;
     for (int j = lane; j < hp.H; j += 32) {
-        const float* wr = hp.vfc1_w + (size_t)j * P0;
+        // vfc1_t is the transposed weight [pos][H]: lanes read consecutive hidden units
         float acc = hp.vfc1_b[j];
-        for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], wr[p], acc);
+        for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], __ldg(hp.vfc1_t + (size_t)p * hp.H + j), acc);
         v = fmaf(fmaxf(acc, 0.f), hp.vfc2_w[j], v);
     }
 #pragma unroll

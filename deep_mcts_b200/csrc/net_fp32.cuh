@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const 
                                                       const u64* second, const u8* player, const float* __restrict__ w,
                                                       const float* __restrict__ bias, int C, float* out_f32,
                                                       __nv_bfloat16* out_bf16, size_t rows_total) {
-    extern __shared__ float smem[];
+    extern __shared__ __align__(16) float smem[];
     const int g = cfg.g, gp = g + 2, P0 = g * g;
     float* s_w = smem;                      // [27][C]
     float* s_b = s_w + 27 * C;              // [C]
@@ -76,18 +76,40 @@ __global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const 
         int y = pos / g, x = pos % g;
         const float* pl = s_planes + bb * 3 * gp * gp;
         float acc[8];
+        if ((C & 7) == 0) {
+            // full chunk: 128-bit shared-memory weight reads (2 per tap and input plane)
+            const float4 bias0 = *reinterpret_cast<const float4*>(s_b + kc * 8);
+            const float4 bias1 = *reinterpret_cast<const float4*>(s_b + kc * 8 + 4);
+            acc[0] = bias0.x; acc[1] = bias0.y; acc[2] = bias0.z; acc[3] = bias0.w;
+            acc[4] = bias1.x; acc[5] = bias1.y; acc[6] = bias1.z; acc[7] = bias1.w;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = (kc * 8 + j < C) ? s_b[kc * 8 + j] : 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            int pp = (y + dy + 1) * gp + (x + dx + 1);
+            for (int tap = 0; tap < 9; ++tap) {
+                const int pp = (y + tap / 3) * gp + (x + tap % 3);
 #pragma unroll
-            for (int ci = 0; ci < 3; ++ci) {
-                float v = pl[ci * gp * gp + pp];
-                const float* wr = s_w + (tap * 3 + ci) * C + kc * 8;
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float v = pl[ci * gp * gp + pp];
+                    const float4 w0 = *reinterpret_cast<const float4*>(s_w + (tap * 3 + ci) * C + kc * 8);
+                    const float4 w1 = *reinterpret_cast<const float4*>(s_w + (tap * 3 + ci) * C + kc * 8 + 4);
+                    acc[0] = fmaf(v, w0.x, acc[0]); acc[1] = fmaf(v, w0.y, acc[1]);
+                    acc[2] = fmaf(v, w0.z, acc[2]); acc[3] = fmaf(v, w0.w, acc[3]);
+                    acc[4] = fmaf(v, w1.x, acc[4]); acc[5] = fmaf(v, w1.y, acc[5]);
+                    acc[6] = fmaf(v, w1.z, acc[6]); acc[7] = fmaf(v, w1.w, acc[7]);
+                }
+            }
+        } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (kc * 8 + j < C) acc[j] = fmaf(v, wr[j], acc[j]);
+            for (int j = 0; j < 8; ++j) acc[j] = (kc * 8 + j < C) ? s_b[kc * 8 + j] : 0.f;
+            for (int tap = 0; tap < 9; ++tap) {
+                int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                int pp = (y + dy + 1) * gp + (x + dx + 1);
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    float v = pl[ci * gp * gp + pp];
+                    const float* wr = s_w + (tap * 3 + ci) * C + kc * 8;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (kc * 8 + j < C) acc[j] = fmaf(v, wr[j], acc[j]);
+                }
             }
         }
 #pragma unroll
@@ -177,6 +199,7 @@ __device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162f
 struct HeadParams {
     const float* pfc_b;   // [A]
     const float* vfc1_w;  // [H][P0]
+    const float* vfc1_t;  // [P0][H] (transposed copy for coalesced reads)
     const float* vfc1_b;  // [H]
     const float* vfc2_w;  // [H]
     float vfc2_b;
