@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample per process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
     return ap.parse_args()
 
 
@@ -61,7 +62,8 @@ def config_block(args, wl, n_gpus):
                     f"{wl['num_simulations']} sims/move, cutoff {wl['sample_move_cutoff']}, "
                     f"dirichlet {wl['dirichlet_alpha']}",
         "step": f"{wl['num_simulations']} search rounds over the pool (one leaf per tree per round)",
-        "trees_per_gpu": args.trees, "num_simulations": wl["num_simulations"], "parallelism": f"games sharded x{n_gpus}",
+        "trees_per_gpu": args.trees, "pools_per_gpu": args.pools, "num_simulations": wl["num_simulations"],
+        "parallelism": f"games sharded x{n_gpus}",
         "l2_policy": "inputs_larger_than_L2 (per-round activations 2x170 MB + GB-scale tree arenas vs 126 MB L2)",
     }
 
@@ -162,8 +164,8 @@ def run_b200(args):
     net.max_batch = args.trees
     sims, T = wl["num_simulations"], args.trees
     engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
-                             replay_capacity=1 << 20, seed=1000 + rank)
-    dn = net.device_net()
+                             replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools)
+    dn = net.device_net()   # e2e leg (full-width batches)
     lib = _lib.load()
 
     def barrier():
@@ -177,7 +179,8 @@ def run_b200(args):
     barrier()
     c0 = engine.counters()
     launches0 = lib.dm_launch_count()
-    dn.profile(True)
+    for pdn in engine.device_nets:
+        pdn.profile(True)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -190,15 +193,19 @@ def run_b200(args):
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     clock_info = clocks.stop() if rank == 0 else None
-    prof = dn.profile_read()
-    dn.profile(False)
+    prof = {}
+    for pdn in engine.device_nets:
+        for k, (ms, cnt) in pdn.profile_read().items():
+            prof[k] = (prof.get(k, (0.0, 0))[0] + ms, prof.get(k, (0.0, 0))[1] + cnt)
+        pdn.profile(False)
     launches = lib.dm_launch_count() - launches0
     c1 = engine.counters()
     d = {k: c1[k] - c0[k] for k in c1}
 
     # ---- end to end through the public batched API with HOST buffers (pinned), fresh roots per step
     from deep_mcts_b200.pool import TreePool, default_node_capacity
-    p, f, s, fin, _ = engine.pool.states()
+    parts = [pl.states() for pl in engine.pools]
+    p, f, s, fin = (np.concatenate([part[i] for part in parts]) for i in range(4))
     keep = ~fin
     idx = np.where(keep)[0]
     idx = np.resize(idx, T)

@@ -20,47 +20,103 @@ from .pool import TreePool, default_node_capacity
 class BatchedSelfPlay:
     def __init__(self, net, n_trees: int, num_simulations: int, sample_move_cutoff: int = 0,
                  dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, replay_capacity: int = 1 << 20,
-                 seed: int = 0, max_nodes_per_tree: Optional[int] = None) -> None:
-        """``net`` is a GameNet (its DeviceNet is used) or a DeviceNet."""
+                 seed: int = 0, max_nodes_per_tree: Optional[int] = None, n_pools: int = 1) -> None:
+        """``net`` is a GameNet (its weights are used) or a DeviceNet.
+
+        ``n_pools`` > 1 splits the games into independent pools, each with its own network
+        buffers and CUDA stream.  The pools' rounds are dependency chains of their own, so the
+        latency-bound tree kernels of one pool run under the tensor-bound network kernels of
+        another (no collective, no data shared between pools)."""
+        if n_trees % n_pools:
+            raise ValueError("n_trees must be divisible by n_pools")
         self.net = net
-        self.device_net: DeviceNet = net if isinstance(net, DeviceNet) else None
         manager = net.manager
-        if self.device_net is None:
-            net.max_batch = max(net.max_batch, n_trees)
-        elif self.device_net.max_batch < n_trees:
-            raise ValueError("DeviceNet.max_batch must be >= n_trees")
+        per_pool = n_trees // n_pools
         cap = max_nodes_per_tree or default_node_capacity(manager, num_simulations)
-        self.pool = TreePool(manager, n_trees, cap, seed=seed)
-        self.pool.configure(num_simulations, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, sample_move_cutoff,
-                            dirichlet_alpha, dirichlet_factor)
-        self.pool.enable_selfplay(replay_capacity)
         self.num_simulations = num_simulations
         self.n_trees = n_trees
+        self.n_pools = n_pools
+        self.pools = []
+        self.device_nets = []
+        for i in range(n_pools):
+            pool = TreePool(manager, per_pool, cap, seed=seed * 1000 + i)
+            pool.configure(num_simulations, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, sample_move_cutoff,
+                           dirichlet_alpha, dirichlet_factor)
+            pool.enable_selfplay(max(1, replay_capacity // n_pools))
+            self.pools.append(pool)
+        if isinstance(net, DeviceNet):
+            if n_pools != 1:
+                raise ValueError("pass a GameNet when n_pools > 1 (each pool needs its own network buffers)")
+            if net.max_batch < per_pool:
+                raise ValueError("DeviceNet.max_batch must be >= trees per pool")
+            self.device_nets = [net]
+        else:
+            self._build_device_nets(per_pool)
+        self.pool = self.pools[0]
+        self.streams = [torch.cuda.Stream(device=self.pool.device) for _ in range(n_pools)] if n_pools > 1 else [None]
 
-    def _dn(self) -> DeviceNet:
-        return self.device_net if self.device_net is not None else self.net.device_net()
+    def _build_device_nets(self, per_pool: int) -> None:
+        net = self.net
+        sd = net.net.state_dict()
+        self.device_nets = []
+        for _ in range(self.n_pools):
+            dn = DeviceNet(net.manager, net.channels, net.num_residual, net.value_head_hidden_units, per_pool,
+                           net.precision)
+            dn.load_state_dict(sd)
+            self.device_nets.append(dn)
+
+    def sync_weights(self) -> None:
+        """Re-pack the GameNet's current weights into every pool's kernels (weight transfer)."""
+        if not isinstance(self.net, DeviceNet):
+            sd = self.net.net.state_dict()
+            for dn in self.device_nets:
+                dn.load_state_dict(sd)
 
     def run_rounds(self, rounds: int) -> None:
-        """``rounds`` x (select one leaf per tree -> network batch -> expand + backup)."""
-        dn = self._dn()
+        """``rounds`` x (select one leaf per tree -> network batch -> expand + backup) for every pool."""
+        if self.n_pools == 1:
+            dn, pool = self.device_nets[0], self.pools[0]
+            for _ in range(int(rounds)):
+                dn.search_round(pool, selfplay=True)
+            return
+        current = torch.cuda.current_stream()
+        for st in self.streams:
+            st.wait_stream(current)
         for _ in range(int(rounds)):
-            dn.search_round(self.pool, selfplay=True)
+            for dn, pool, st in zip(self.device_nets, self.pools, self.streams):
+                with torch.cuda.stream(st):
+                    dn.search_round(pool, selfplay=True)
+        for st in self.streams:
+            current.wait_stream(st)
 
     def counters(self) -> dict:
-        return self.pool.counters()
+        total = None
+        for pool in self.pools:
+            c = pool.counters()
+            if total is None:
+                total = dict(c)
+            else:
+                for k, v in c.items():
+                    total[k] = max(total[k], v) if k == "nodes_high_water" else total[k] + v
+        return total
 
     def positions_written(self) -> int:
-        return int(self.pool.replay_written.item())
+        return sum(int(pool.replay_written.item()) for pool in self.pools)
 
     def sample_batch(self, batch_size: int, generator: Optional[torch.Generator] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Uniform sample over the replay ring: (first, second, player, pi[B, A], z[B, 1]) on the device
+        """Uniform sample over the replay rings: (first, second, player, pi[B, A], z[B, 1]) on the device
         (reference train.py:337-348 samples uniformly over positions)."""
-        written = self.positions_written()
-        n = min(written, self.pool.replay_capacity)
-        if n == 0:
+        sizes = [min(int(pool.replay_written.item()), pool.replay_capacity) for pool in self.pools]
+        total = sum(sizes)
+        if total == 0:
             raise RuntimeError("replay ring is empty")
-        idx = torch.randint(0, n, (batch_size,), device=self.pool.device, generator=generator)
+        dev = self.pool.device
+        idx = torch.randint(0, total, (batch_size,), device=dev, generator=generator)
         A = self.pool.num_actions
-        return (self.pool.replay_first[idx], self.pool.replay_second[idx], self.pool.replay_player[idx],
-                self.pool.replay_pi[idx, :A], self.pool.replay_z[idx].unsqueeze(1))
+        first = torch.cat([p.replay_first[:n] for p, n in zip(self.pools, sizes)])
+        second = torch.cat([p.replay_second[:n] for p, n in zip(self.pools, sizes)])
+        player = torch.cat([p.replay_player[:n] for p, n in zip(self.pools, sizes)])
+        pi = torch.cat([p.replay_pi[:n, :A] for p, n in zip(self.pools, sizes)])
+        z = torch.cat([p.replay_z[:n] for p, n in zip(self.pools, sizes)])
+        return first[idx], second[idx], player[idx], pi[idx], z[idx].unsqueeze(1)
