@@ -248,13 +248,12 @@ def run_b200(args):
     d2h = T * (_lib.DM_MAX_ACTIONS * 4 + 8)
 
     # ---- reduce over ranks: sums of work, max of time
-    vals = torch.tensor([d["simulations"], d["leaf_evals"], e2e_sims, launches], dtype=torch.float64, device="cuda")
-    times = torch.tensor([elapsed_ms, e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(vals, op=dist.ReduceOp.SUM)
-        dist.all_reduce(times, op=dist.ReduceOp.MAX)
-    tot_sims, tot_evals, tot_e2e_sims, tot_launches = (float(v) for v in vals.tolist())
-    elapsed_ms, e2e_ms = (float(v) for v in times.tolist())
+    from deep_mcts_b200.distributed import reduce_counters
+    sums, maxima = reduce_counters(
+        {"sims": d["simulations"], "evals": d["leaf_evals"], "e2e_sims": e2e_sims, "launches": launches},
+        {"elapsed_ms": elapsed_ms, "e2e_ms": e2e_ms}, "cuda")
+    tot_sims, tot_evals, tot_e2e_sims, tot_launches = sums["sims"], sums["evals"], sums["e2e_sims"], sums["launches"]
+    elapsed_ms, e2e_ms = maxima["elapsed_ms"], maxima["e2e_ms"]
 
     if rank == 0:
         g = wl["grid"]

@@ -61,6 +61,7 @@ _SIGNATURES = {
     "dm_game_child": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dm_game_status": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "dm_game_rollout": (c_int, [c_int, c_int, c_int, _P, _P, _P, c_int, c_uint64, _P, _P, _P]),
+    "dm_eval_uniform": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
     "dm_pool_create": (c_int, [POINTER(PoolConfig), POINTER(c_void_p)]),
     "dm_pool_destroy": (c_int, [_P]),
     "dm_pool_configure": (c_int, [_P, POINTER(SearchConfig)]),

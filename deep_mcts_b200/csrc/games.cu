@@ -83,7 +83,41 @@ __global__ void k_game_rollout(GameCfg cfg, int n, const u64* first, const u64* 
     if (plies) plies[i] = p;
 }
 
+// uniform_state_evaluator (reference train.py:240-248): value 0.5, 1/len(legal) on legal actions
+__global__ void k_eval_uniform(GameCfg cfg, int n, const int* count_dev, const u64* first, const u64* second,
+                               const u8* player, float* value, float* probs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int live = count_dev ? min(*count_dev, n) : n;
+    if (i >= live) return;
+    GState s;
+    s.first = first[i];
+    s.second = second[i];
+    s.player = player[i];
+    bool extra;
+    u64 m = game_legal_mask(cfg, s, extra);
+    int cnt = __popcll(m) + (extra ? 1 : 0);
+    float p = cnt ? (float)(1.0 / (double)cnt) : 0.f;
+    float* row = probs + (size_t)i * DM_MAX_ACTIONS;
+    for (int a = 0; a < DM_MAX_ACTIONS; ++a)
+        row[a] = (a < cfg.cells ? ((m >> a) & 1) : (a == cfg.cells && extra)) ? p : 0.f;
+    value[i] = 0.5f;
+}
+
 }  // namespace
+
+extern "C" int dm_eval_uniform(int game, int grid, int n, const int32_t* count_dev, const uint64_t* first,
+                               const uint64_t* second, const uint8_t* player, float* value, float* probs,
+                               void* stream) {
+    DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_eval_uniform: unsupported game/grid");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
+    if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player && value && probs, "dm_eval_uniform: bad arguments");
+    k_eval_uniform<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_game_cfg(game, grid), n, count_dev,
+                                                                      (const u64*)first, (const u64*)second, player,
+                                                                      value, probs);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
 
 extern "C" int dm_game_num_actions(int game, int grid) {
     if (!game_cfg_valid(game, grid)) {

@@ -56,6 +56,9 @@ class GameNet(ABC):
         self._device_net: Optional[DeviceNet] = None
         self._device_net_stale = True
         self.precision: Optional[str] = None  # None = bf16 when the architecture allows, else fp32
+        # optional hook run between backward() and optimizer.step(), e.g.
+        # deep_mcts_b200.distributed.allreduce_gradients for data-parallel training
+        self.grad_sync: Optional[Callable] = None
         self.max_batch = 4096
         # lets MCTS recognise `net.evaluate` as a device evaluator
         self._dm_net_self = self
@@ -110,6 +113,8 @@ class GameNet(ABC):
         acc = accuracy(logits, probability_targets)
         self.optimizer.zero_grad()
         (policy_loss + value_loss).backward()
+        if self.grad_sync is not None:
+            self.grad_sync(self.net.parameters())
         self.optimizer.step()
         self._device_net_stale = True
         return policy_loss, value_loss, acc

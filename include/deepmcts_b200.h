@@ -122,6 +122,13 @@ int dm_game_rollout(int game, int grid, int n, const uint64_t* first_dev, const 
                     const uint8_t* player_dev, int rollout_kind, uint64_t seed, float* outcome_dev,
                     int32_t* plies_dev, void* stream);
 
+/* uniform_state_evaluator (train.py:240-248) for a leaf batch: value_dev[n] = 0.5 and
+ * probs_dev[n][DM_MAX_ACTIONS] = 1/len(legal) on legal actions; count_dev (may be NULL) is the
+ * live batch size on the device. */
+int dm_eval_uniform(int game, int grid, int n, const int32_t* count_dev, const uint64_t* first_dev,
+                    const uint64_t* second_dev, const uint8_t* player_dev, float* value_dev, float* probs_dev,
+                    void* stream);
+
 /* ------------------------------------------------------------------------ trees */
 int dm_pool_create(const dm_pool_config* cfg, dm_pool** out);
 int dm_pool_destroy(dm_pool* pool);
