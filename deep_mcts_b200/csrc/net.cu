@@ -200,8 +200,11 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         return DM_ERR_INVALID;
     }
     int pe = prof_begin(net, 0, st);
-    netk::k_encode_conv1<true><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player, net->conv1_w,
-                                                                  net->conv1_b, C, nullptr, net->a0, net->rows_total);
+    {
+        size_t smem2 = (size_t)(27 * C + C + 16 * C) * sizeof(float) + (size_t)netk::kEncode2Boards * gp * gp + 16;
+        netk::k_encode_conv1_sparse<<<(n + netk::kEncode2Boards - 1) / netk::kEncode2Boards, 256, smem2, st>>>(
+            g, n, count_dev, first, second, player, net->conv1_w, net->conv1_b, C, net->a0, net->rows_total);
+    }
     prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
     const bool v1 = net->conv_v1;
@@ -376,6 +379,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                      (int)netk::conv_smem_bytes(net->geom)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv2_smem_bytes(net->geom)));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((27 * C + C + 16 * C) * sizeof(float) + netk::kEncode2Boards * (g + 2) * (g + 2) + 16)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_policy_fc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::fc_smem_bytes(net->fc_na)));
         net->bf16_ready = true;

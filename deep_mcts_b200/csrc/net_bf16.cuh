@@ -296,13 +296,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
 // TMEM: accumulator (buf, tile) at column (buf*2 + tile) * 128.
 constexpr int kItemTiles = 2;
 constexpr int kItemRows = kTileM * kItemTiles;  // 256
-constexpr int kStages2 = 2;
+// weight ring: stages of kStageK16 K-steps (one K-step = 16 input channels of one tap = 4 KB).
+// Small stages keep many loads in flight: a stage is refilled only after the MMAs that read it
+// retire, so with two whole-tap stages the tensor core waited ~0.8k cycles per tap for L2.
+constexpr int kStageK16 = 2;
+constexpr int kStage2Bytes = kStageK16 * 2 * kC * 16;   // 8 KB
+constexpr int kStages2 = 8;
+constexpr int kStagesPerTap = (kC / 16) / kStageK16;    // 4
 constexpr int kConv2Threads = 224;
 
 __host__ __device__ inline int conv2_a_rows(const RowGeom& geom) { return kItemRows + 2 * geom.halo; }
 inline size_t conv2_smem_bytes(const RowGeom& geom) {
-    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStageBytes + 2 * kC * sizeof(float) +
-           256;
+    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStage2Bytes + 2 * kC * sizeof(float) +
+           512;
 }
 inline size_t conv2_rows_total(const RowGeom& geom, int n_boards) {
     size_t body = ((size_t)n_boards * geom.P + kItemRows - 1) / kItemRows * kItemRows;
@@ -324,8 +330,8 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
     const u32 a_buf_bytes = (u32)kChunks * a_rows * 16;
     unsigned char* s_a = base;                                  // [2][16][a_rows][16 B]
-    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][32 KB]
-    float* s_bias = (float*)(s_b + (size_t)kStages2 * kStageBytes);
+    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][8 KB]
+    float* s_bias = (float*)(s_b + (size_t)kStages2 * kStage2Bytes);
     float* s_vw = s_bias + kC;
     u64* s_bar = (u64*)(s_vw + kC);
     // barriers: b_full[S], b_empty[S], a_full[2], a_empty[2], acc_full[2], acc_empty[2]
@@ -368,11 +374,12 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
             // ---- weight producer
             int s = 0;
             for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                for (int tap = 0; tap < 9; ++tap, ++s) {
+                for (int part = 0; part < 9 * kStagesPerTap; ++part, ++s) {   // weights are contiguous per part
                     int st = s % kStages2;
                     if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
-                    mbar_expect_tx(bar_bfull + 8 * st, kStageBytes);
-                    bulk_g2s(smem_u32(s_b + (size_t)st * kStageBytes), args.w + (size_t)tap * kC * kC, kStageBytes,
+                    mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
+                    bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes),
+                             reinterpret_cast<const unsigned char*>(args.w) + (size_t)part * kStage2Bytes, kStage2Bytes,
                              bar_bfull + 8 * st);
                 }
             }
@@ -403,24 +410,27 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                 if (j >= 2) mbar_wait(bar_accempty + 8 * buf, ((j >> 1) - 1) & 1);
                 tc_fence_after();
                 const u32 a_base = smem_u32(s_a + (size_t)buf * a_buf_bytes);
-                for (int tap = 0; tap < 9; ++tap, ++s) {
-                    int st = s % kStages2;
-                    mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
-                    tc_fence_after();
+                for (int tap = 0; tap < 9; ++tap) {
                     const int shift = (tap / 3 - 1) * geom.Wp + (tap % 3 - 1);
-                    const u32 b_addr = smem_u32(s_b + (size_t)st * kStageBytes);
+                    for (int part = 0; part < kStagesPerTap; ++part, ++s) {
+                        int st = s % kStages2;
+                        mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
+                        tc_fence_after();
+                        const u32 b_addr = smem_u32(s_b + (size_t)st * kStage2Bytes);
 #pragma unroll
-                    for (int tile = 0; tile < kItemTiles; ++tile) {
-                        const u32 a_addr = a_base + (u32)(geom.halo + tile * kTileM + shift) * 16;
+                        for (int tile = 0; tile < kItemTiles; ++tile) {
+                            const u32 a_addr = a_base + (u32)(geom.halo + tile * kTileM + shift) * 16;
 #pragma unroll
-                        for (int k16 = 0; k16 < kC / 16; ++k16) {
-                            u64 ad = umma_desc(a_addr + (u32)(2 * k16) * lbo_a, lbo_a, sbo);
-                            u64 bd = umma_desc(b_addr + (u32)(2 * k16) * lbo_b, lbo_b, sbo);
-                            tc_mma_bf16(tmem_base + (u32)((buf * kItemTiles + tile) * kC), ad, bd, kIdescBf16,
-                                        (tap | k16) ? 1u : 0u);
+                            for (int kk = 0; kk < kStageK16; ++kk) {
+                                const int k16 = part * kStageK16 + kk;
+                                u64 ad = umma_desc(a_addr + (u32)(2 * k16) * lbo_a, lbo_a, sbo);
+                                u64 bd = umma_desc(b_addr + (u32)(2 * kk) * lbo_b, lbo_b, sbo);
+                                tc_mma_bf16(tmem_base + (u32)((buf * kItemTiles + tile) * kC), ad, bd, kIdescBf16,
+                                            (tap | k16) ? 1u : 0u);
+                            }
                         }
+                        tc_commit(bar_bempty + 8 * st);
                     }
-                    tc_commit(bar_bempty + 8 * st);
                 }
                 tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
                 tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled

@@ -1,0 +1,97 @@
+"""GPU parity of the continuous self-play kernels (move choice, re-rooting with subtree reuse,
+example recording, outcome labelling, restart) against the oracle's MCTS.self_play +
+create_self_play_examples semantics (reference mcts.py:96-111, train.py:258-283)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import evaluators as oev
+from oracle.games import make_game
+from oracle.mcts import OracleMCTS
+
+pytestmark = pytest.mark.gpu
+
+from test_games_gpu import manager_for  # noqa: E402
+
+
+def host_round(pool, game, evaluator):
+    """One self-play round with a HOST evaluator plugged into the leaf exchange."""
+    from deep_mcts_b200 import _lib
+    pool.selfplay_select()
+    n = int(pool.leaf_count.item())
+    T = pool.n_trees
+    pri = np.zeros((T, _lib.DM_MAX_ACTIONS), np.float64)
+    val = np.zeros(T, np.float64)
+    if n:
+        p = pool.leaf_player[:n].cpu().numpy()
+        f = pool.leaf_first[:n].cpu().numpy().view(np.uint64)
+        s = pool.leaf_second[:n].cpu().numpy().view(np.uint64)
+        for i in range(n):
+            v, probs = evaluator(game, (int(p[i]), int(f[i]), int(s[i])))
+            val[i] = v
+            pri[i, : game.num_actions] = probs
+    pool.expand_backup(torch.from_numpy(pri).to(pool.device), torch.from_numpy(val).to(pool.device))
+    return n
+
+
+@pytest.mark.parametrize("name,g,sims", [("othello", 6, 30), ("hex_with_swap", 4, 25), ("tictactoe", 3, 20)])
+def test_selfplay_games_match_oracle(name, g, sims):
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200.pool import TreePool
+    game = make_game(name, g)
+    manager = manager_for(name, g)
+    T = 3
+    pool = TreePool(manager, T, 1 << 15, seed=5)
+    pool.configure(sims, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, 0, 0.0, 0.25)   # cutoff 0, no noise: deterministic
+    pool.enable_selfplay(4096)
+    # oracle: one full deterministic game (all trees play the same game, then restart and repeat it)
+    ref = OracleMCTS(game, sims, None, oev.hashed)
+    examples = [(old, dist) for old, new, action, dist in ref.self_play()]
+    outcome = game.outcome(ref.state)
+    plies = len(examples)
+    # enough rounds for every tree to finish one game (+ slack for root expansions / terminal sims)
+    for _ in range(plies * (sims + 2) + 5):
+        host_round(pool, game, oev.hashed)
+        if pool.counters()["games"] >= T:
+            break
+    c = pool.counters()
+    assert c["games"] >= T and c["capacity_errors"] == 0
+    written = int(pool.replay_written.item())
+    assert written >= T * plies
+    first = pool.replay_first[:written].cpu().numpy().view(np.uint64)
+    second = pool.replay_second[:written].cpu().numpy().view(np.uint64)
+    player = pool.replay_player[:written].cpu().numpy()
+    pi = pool.replay_pi[:written].cpu().numpy()
+    z = pool.replay_z[:written].cpu().numpy()
+    z_abs = outcome * 2 - 1
+    for t in range(T):   # every tree wrote one contiguous game
+        for i, (state, dist) in enumerate(examples):
+            r = t * plies + i
+            assert (int(player[r]), int(first[r]), int(second[r])) == state
+            np.testing.assert_array_equal(pi[r, : game.num_actions], np.asarray(dist, np.float32))
+            assert z[r] == (z_abs if state[0] == 0 else -z_abs)   # train.py:270-282
+
+
+def test_selfplay_with_device_net_runs_and_labels_consistently():
+    from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
+    from deep_mcts_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ConvolutionalOthelloNet(4)
+    engine = BatchedSelfPlay(net, 256, 8, sample_move_cutoff=4, dirichlet_alpha=1.0, replay_capacity=1 << 16, seed=3)
+    engine.run_rounds(400)
+    c = engine.counters()
+    assert c["games"] > 100 and c["capacity_errors"] == 0 and c["moves"] > c["games"] * 4
+    n = min(engine.positions_written(), 1 << 16)
+    pool = engine.pool
+    pi = pool.replay_pi[:n, :17].cpu().numpy()
+    z = pool.replay_z[:n].cpu().numpy()
+    np.testing.assert_allclose(pi.sum(axis=1), 1.0, atol=1e-5)
+    assert set(np.unique(z)).issubset({-1.0, 0.0, 1.0}) and (z != 0).any()
+    f, s, p, pi_b, z_b = engine.sample_batch(64)
+    assert pi_b.shape == (64, 17) and z_b.shape == (64, 1) and f.is_cuda
+    # multi-pool variant
+    engine2 = BatchedSelfPlay(net, 256, 8, sample_move_cutoff=4, dirichlet_alpha=1.0, replay_capacity=1 << 16,
+                              seed=4, n_pools=2)
+    engine2.run_rounds(100)
+    torch.cuda.synchronize()
+    assert engine2.counters()["games"] > 10
