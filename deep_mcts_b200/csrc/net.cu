@@ -29,6 +29,8 @@ struct dm_net {
     std::vector<float*> trunk_w, trunk_b;
     float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_t = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
     float vconv_b = 0.f, vfc2_b = 0.f;
+    std::vector<std::vector<float>> h_trunk_b;  // host copies for by-value kernel parameters
+    std::vector<float> h_vconv_w;
     // bf16 weights
     std::vector<__nv_bfloat16*> trunk_w16;
     __nv_bfloat16* pfc_w16 = nullptr;  // [g*g*16][NA][8] (k_policy_fc_tc B operand)
@@ -223,6 +225,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     for (int i = 0; i < R; ++i) {
         a.in = net->a0; a.out = net->a1; a.out_nhwc = nullptr; a.residual = nullptr;
         a.w = net->trunk_w16[2 * i]; a.bias = net->trunk_b[2 * i]; a.vhead_w = nullptr; a.vplane = nullptr;
+        memcpy(a.bias_c, net->h_trunk_b[2 * i].data(), sizeof(a.bias_c));
         {
             int pc = prof_begin(net, 1, st);
             conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
@@ -231,8 +234,10 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         DM_LAUNCH_CHECK();
         a.in = net->a1; a.out = net->a0; a.residual = net->a0;
         a.w = net->trunk_w16[2 * i + 1]; a.bias = net->trunk_b[2 * i + 1];
+        memcpy(a.bias_c, net->h_trunk_b[2 * i + 1].data(), sizeof(a.bias_c));
         if (i == R - 1) {
             a.vhead_w = net->vconv_w; a.vhead_b = net->vconv_b; a.vplane = net->vplane;
+            memcpy(a.vw_c, net->h_vconv_w.data(), sizeof(a.vw_c));
         }
         {
             int pc = prof_begin(net, 1, st);
@@ -243,6 +248,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     }
     a.in = net->a0; a.out = nullptr; a.out_nhwc = nullptr; a.out_fc = net->t16; a.residual = nullptr;
     a.w = net->trunk_w16[L - 1]; a.bias = net->trunk_b[L - 1]; a.vhead_w = nullptr; a.vplane = nullptr;
+    memcpy(a.bias_c, net->h_trunk_b[L - 1].data(), sizeof(a.bias_c));
     {
         int pc = prof_begin(net, 1, st);
         conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
@@ -319,6 +325,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
         DM_TRY(net_upload(net, &net->trunk_w[l], hw.trunk_w[l]));
         DM_TRY(net_upload(net, &net->trunk_b[l], hw.trunk_b[l]));
     }
+    net->h_trunk_b = hw.trunk_b;
+    net->h_vconv_w = hw.vconv_w;
     DM_TRY(net_upload(net, &net->vconv_w, hw.vconv_w));
     net->vconv_b = hw.vconv_b;
     DM_TRY(net_upload(net, &net->vfc1_w, hw.vfc1_w));

@@ -42,6 +42,11 @@ struct ConvArgs {
     const float* bias;              // [128]
     const float* vhead_w;           // [128] or null: also emit the value-head 1x1 conv
     float vhead_b;
+    // Host copies of the two vectors above, passed BY VALUE: kernel parameters live in the constant
+    // bank, so the epilogue's per-channel operands become c[0x0][imm] immediates and never touch
+    // the shared-memory data pipe, which tcgen05.mma (SS mode, 128 B/clk of operands) needs whole.
+    float bias_c[128];
+    float vw_c[128];
     float* vplane;                  // [n][g*g]
     size_t rows_total;
     int n_boards;
@@ -121,6 +126,25 @@ __device__ __forceinline__ u64 umma_desc(u32 saddr, u32 lbo_bytes, u32 sbo_bytes
     return (u64)((saddr & 0x3FFFFu) >> 4) | ((u64)((lbo_bytes >> 4) & 0x3FFF) << 16) |
            ((u64)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
 }
+// The same descriptor split in two 32-bit halves so that advancing along K or M is one 32-bit add
+// on the low word (start-address field, units of 16 bytes; never carries into the LBO field).
+__device__ __forceinline__ u32 umma_desc_lo(u32 saddr, u32 lbo_bytes) {
+    return ((saddr & 0x3FFFFu) >> 4) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ u32 umma_desc_hi(u32 sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
+__device__ __forceinline__ u64 umma_desc_join(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
+
+// one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+    u32 pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // instruction descriptor: D fp32, A/B bf16, both K-major, N = 128, M = 128
 constexpr u32 kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((u32)(kC >> 3) << 17) | ((u32)(kTileM >> 4) << 24);
 
@@ -296,19 +320,13 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
 // TMEM: accumulator (buf, tile) at column (buf*2 + tile) * 128.
 constexpr int kItemTiles = 2;
 constexpr int kItemRows = kTileM * kItemTiles;  // 256
-// weight ring: stages of kStageK16 K-steps (one K-step = 16 input channels of one tap = 4 KB).
-// Small stages keep many loads in flight: a stage is refilled only after the MMAs that read it
-// retire, so with two whole-tap stages the tensor core waited ~0.8k cycles per tap for L2.
-constexpr int kStageK16 = 2;
-constexpr int kStage2Bytes = kStageK16 * 2 * kC * 16;   // 8 KB
-constexpr int kStages2 = 8;
-constexpr int kStagesPerTap = (kC / 16) / kStageK16;    // 4
+constexpr int kStages2 = 2;
 constexpr int kConv2Threads = 224;
 
 __host__ __device__ inline int conv2_a_rows(const RowGeom& geom) { return kItemRows + 2 * geom.halo; }
 inline size_t conv2_smem_bytes(const RowGeom& geom) {
-    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStage2Bytes + 2 * kC * sizeof(float) +
-           512;
+    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStageBytes + 2 * kC * sizeof(float) +
+           256;
 }
 inline size_t conv2_rows_total(const RowGeom& geom, int n_boards) {
     size_t body = ((size_t)n_boards * geom.P + kItemRows - 1) / kItemRows * kItemRows;
@@ -330,8 +348,8 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
     const u32 a_buf_bytes = (u32)kChunks * a_rows * 16;
     unsigned char* s_a = base;                                  // [2][16][a_rows][16 B]
-    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][8 KB]
-    float* s_bias = (float*)(s_b + (size_t)kStages2 * kStage2Bytes);
+    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][32 KB]
+    float* s_bias = (float*)(s_b + (size_t)kStages2 * kStageBytes);
     float* s_vw = s_bias + kC;
     u64* s_bar = (u64*)(s_vw + kC);
     // barriers: b_full[S], b_empty[S], a_full[2], a_empty[2], acc_full[2], acc_empty[2]
@@ -340,7 +358,10 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     const u32 bar_accfull = smem_u32(&s_bar[2 * kStages2 + 4]), bar_accempty = smem_u32(&s_bar[2 * kStages2 + 6]);
     u32* s_tmem = (u32*)(s_bar + 2 * kStages2 + 8);
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warp-uniform role index (the shuffle lets the compiler prove uniformity, so the issue loops
+    // below run on the uniform datapath instead of R2UR waterfalls around every UTCHMMA)
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x; i < kC; i += blockDim.x) {
         s_bias[i] = args.bias[i];
         s_vw[i] = args.vhead_w ? args.vhead_w[i] : 0.f;
@@ -370,70 +391,74 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     const u32 tmem_base = *s_tmem;
 
     if (warp == 0) {
-        if (lane == 0) {
-            // ---- weight producer
-            int s = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-                for (int part = 0; part < 9 * kStagesPerTap; ++part, ++s) {   // weights are contiguous per part
-                    int st = s % kStages2;
-                    if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
-                    mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
-                    bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes),
-                             reinterpret_cast<const unsigned char*>(args.w) + (size_t)part * kStage2Bytes, kStage2Bytes,
+        // ---- weight producer (whole warp runs the loop; one elected lane issues)
+        int s = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            for (int tap = 0; tap < 9; ++tap, ++s) {
+                const int st = s % kStages2;
+                if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
+                if (elect_one()) {
+                    mbar_expect_tx(bar_bfull + 8 * st, kStageBytes);
+                    bulk_g2s(smem_u32(s_b + (size_t)st * kStageBytes), args.w + (size_t)tap * kC * kC, kStageBytes,
                              bar_bfull + 8 * st);
                 }
+                __syncwarp();
             }
         }
     } else if (warp == 2) {
-        if (lane == 0) {
-            // ---- activation producer
-            const u32 a_chunk_bytes = (u32)a_rows * 16;
-            int j = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-                int buf = j & 1;
-                if (j >= 2) mbar_wait(bar_aempty + 8 * buf, ((j >> 1) - 1) & 1);
+        // ---- activation producer
+        const u32 a_chunk_bytes = (u32)a_rows * 16;
+        int j = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            const int buf = j & 1;
+            if (j >= 2) mbar_wait(bar_aempty + 8 * buf, ((j >> 1) - 1) & 1);
+            const size_t row0 = (size_t)it * kItemRows;
+            if (elect_one()) {
                 mbar_expect_tx(bar_afull + 8 * buf, a_chunk_bytes * kChunks);
-                const size_t row0 = (size_t)it * kItemRows;
                 for (int kc = 0; kc < kChunks; ++kc)
                     bulk_g2s(smem_u32(s_a + (size_t)buf * a_buf_bytes + (size_t)kc * a_chunk_bytes),
                              args.in + ((size_t)kc * args.rows_total + row0) * 8, a_chunk_bytes, bar_afull + 8 * buf);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---- MMA issuer
-            const u32 lbo_a = (u32)a_rows * 16, lbo_b = kC * 16, sbo = 128;
-            int j = 0, s = 0;
-            for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
-                int buf = j & 1;
-                mbar_wait(bar_afull + 8 * buf, (j >> 1) & 1);
-                if (j >= 2) mbar_wait(bar_accempty + 8 * buf, ((j >> 1) - 1) & 1);
+        // ---- MMA issuer: the whole warp walks the loop, one elected lane issues each instruction
+        const u32 lbo_a = (u32)a_rows * 16, lbo_b = kC * 16;
+        const u32 desc_hi = umma_desc_hi(128);
+        const u32 a_k16_step = (2 * lbo_a) >> 4, b_k16_step = (2 * lbo_b) >> 4;  // descriptor units (16 B)
+        int j = 0, s = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            const int buf = j & 1;
+            mbar_wait(bar_afull + 8 * buf, (j >> 1) & 1);
+            if (j >= 2) mbar_wait(bar_accempty + 8 * buf, ((j >> 1) - 1) & 1);
+            tc_fence_after();
+            const u32 a_lo_base = umma_desc_lo(smem_u32(s_a + (size_t)buf * a_buf_bytes), lbo_a) + (u32)geom.halo;
+            const u32 d_base = tmem_base + (u32)(buf * kItemTiles * kC);
+            for (int tap = 0; tap < 9; ++tap, ++s) {
+                const int st = s % kStages2;
+                mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
                 tc_fence_after();
-                const u32 a_base = smem_u32(s_a + (size_t)buf * a_buf_bytes);
-                for (int tap = 0; tap < 9; ++tap) {
-                    const int shift = (tap / 3 - 1) * geom.Wp + (tap % 3 - 1);
-                    for (int part = 0; part < kStagesPerTap; ++part, ++s) {
-                        int st = s % kStages2;
-                        mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
-                        tc_fence_after();
-                        const u32 b_addr = smem_u32(s_b + (size_t)st * kStage2Bytes);
+                const int shift = (tap / 3 - 1) * geom.Wp + (tap % 3 - 1);   // rows == descriptor units
+                const u32 a_lo_tap = a_lo_base + (u32)shift;
+                const u32 b_lo_tap = umma_desc_lo(smem_u32(s_b + (size_t)st * kStageBytes), lbo_b);
+                if (elect_one()) {
 #pragma unroll
-                        for (int tile = 0; tile < kItemTiles; ++tile) {
-                            const u32 a_addr = a_base + (u32)(geom.halo + tile * kTileM + shift) * 16;
+                    for (int tile = 0; tile < kItemTiles; ++tile) {
 #pragma unroll
-                            for (int kk = 0; kk < kStageK16; ++kk) {
-                                const int k16 = part * kStageK16 + kk;
-                                u64 ad = umma_desc(a_addr + (u32)(2 * k16) * lbo_a, lbo_a, sbo);
-                                u64 bd = umma_desc(b_addr + (u32)(2 * kk) * lbo_b, lbo_b, sbo);
-                                tc_mma_bf16(tmem_base + (u32)((buf * kItemTiles + tile) * kC), ad, bd, kIdescBf16,
-                                            (tap | k16) ? 1u : 0u);
-                            }
+                        for (int k16 = 0; k16 < kC / 16; ++k16) {
+                            tc_mma_bf16(d_base + (u32)(tile * kC),
+                                        umma_desc_join(a_lo_tap + (u32)(tile * kTileM) + (u32)k16 * a_k16_step, desc_hi),
+                                        umma_desc_join(b_lo_tap + (u32)k16 * b_k16_step, desc_hi), kIdescBf16,
+                                        (tap | k16) ? 1u : 0u);
                         }
-                        tc_commit(bar_bempty + 8 * st);
+                    }
+                    tc_commit(bar_bempty + 8 * st);
+                    if (tap == 8) {
+                        tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
+                        tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled
                     }
                 }
-                tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
-                tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled
+                __syncwarp();
             }
         }
     } else {
@@ -471,7 +496,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                     if (valid) {
                         float f[32];
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(v[jj]) + s_bias[cc * 32 + jj];
+                        for (int jj = 0; jj < 32; ++jj) f[jj] = __uint_as_float(v[jj]) + args.bias_c[cc * 32 + jj];
                         if (args.residual) {
 #pragma unroll
                             for (int c4 = 0; c4 < 4; ++c4) {
@@ -485,9 +510,10 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                             }
                         }
 #pragma unroll
-                        for (int jj = 0; jj < 32; ++jj) {
-                            f[jj] = fmaxf(f[jj], 0.f);
-                            vacc = fmaf(f[jj], s_vw[cc * 32 + jj], vacc);
+                        for (int jj = 0; jj < 32; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+                        if (args.vhead_w) {
+#pragma unroll
+                            for (int jj = 0; jj < 32; ++jj) vacc = fmaf(f[jj], args.vw_c[cc * 32 + jj], vacc);
                         }
 #pragma unroll
                         for (int c4 = 0; c4 < 4; ++c4) {
