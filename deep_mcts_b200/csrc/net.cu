@@ -260,7 +260,8 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     int ph = prof_begin(net, 2, st);
     netk::k_policy_fc_tc<<<dim3((n + 127) / 128, net->fc_split), netk::kFcThreads, netk::fc_smem_bytes(net->fc_na), st>>>(fa);
     ++g_dm_launches;
-    netk::k_heads_finish<<<(n + 3) / 4, 128, 0, st>>>(g, n, count_dev, first, second, player, net->fc_partial,
+    netk::k_heads_finish<<<(n + netk::kFinishBoards - 1) / netk::kFinishBoards, netk::kFinishBoards * 32,
+                           (size_t)P0 * net->cfg.hidden * sizeof(float), st>>>(g, n, count_dev, first, second, player, net->fc_partial,
                                                      net->fc_split, n_cap, net->fc_na, net->vplane, hp, mode,
                                                      value_out, probs_out);
     prof_end(net, ph, st);
@@ -389,6 +390,9 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                      (int)netk::conv2_smem_bytes(net->geom)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((27 * C + C + 16 * C) * sizeof(float) + netk::kEncode2Boards * (g + 2) * (g + 2) + 16)));
+        DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");
+        DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)P0 * H * sizeof(float))));
         DM_CUDA(cudaFuncSetAttribute(netk::k_policy_fc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::fc_smem_bytes(net->fc_na)));
         net->bf16_ready = true;

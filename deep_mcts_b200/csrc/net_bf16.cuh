@@ -685,16 +685,22 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_policy_fc_tc(FcArgs args) {
 
 // Sums the split-K partial logits, runs the value-head FCs and GameNet.evaluate's
 // post-processing (gamenet.py:67-85).  One warp per board.
-__global__ void __launch_bounds__(128) k_heads_finish(GameCfg cfg, int n, const int* count_dev, const u64* first,
+constexpr int kFinishBoards = 8;
+__global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg, int n, const int* count_dev, const u64* first,
                                                       const u64* second, const u8* player,
                                                       const float* __restrict__ partial, int split, int n_cap, int NA,
                                                       const float* __restrict__ vplane, HeadParams hp, int mode,
                                                       float* value_out, float* probs_out) {
-    __shared__ float s_vp[4][64];
+    extern __shared__ __align__(16) float s_w1[];  // [P0][H] transposed value-FC1 weights
+    __shared__ float s_vp[kFinishBoards][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int gb = blockIdx.x * 4 + warp;
-    if (gb >= live_count(count_dev, n)) return;
+    const int gb = blockIdx.x * kFinishBoards + warp;
     const int P0 = cfg.g * cfg.g, A = cfg.num_actions;
+    const int live = live_count(count_dev, n);
+    if (blockIdx.x * kFinishBoards >= live) return;
+    for (int i = threadIdx.x; i < P0 * hp.H; i += blockDim.x) s_w1[i] = hp.vfc1_t[i];
+    __syncthreads();
+    if (gb >= live) return;
     GState s;
     s.first = first[gb];
     s.second = second[gb];
@@ -705,7 +711,7 @@ __global__ void __launch_bounds__(128) k_heads_finish(GameCfg cfg, int n, const 
     for (int j = lane; j < hp.H; j += 32) {
         // vfc1_t is the transposed weight [pos][H]: lanes read consecutive hidden units
         float acc = hp.vfc1_b[j];
-        for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], __ldg(hp.vfc1_t + (size_t)p * hp.H + j), acc);
+        for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], s_w1[p * hp.H + j], acc);
         v = fmaf(fmaxf(acc, 0.f), hp.vfc2_w[j], v);
     }
 #pragma unroll

@@ -189,45 +189,51 @@ __global__ void __launch_bounds__(256) k_encode_conv1_sparse(GameCfg cfg, int n,
     __syncthreads();
     const RowGeom geom = RowGeom::make(g);
     const int chunks = C / 8;
-    const int items = kEncode2Boards * P0 * chunks;
-    for (int it = threadIdx.x; it < items; it += blockDim.x) {
-        int pos = it % P0, rest = it / P0;
-        int kc = rest % chunks, bb = rest / chunks;
-        int b = b0 + bb;
-        if (b >= live) continue;
-        int y = pos / g, x = pos % g;
-        float4 a0 = *reinterpret_cast<const float4*>(s_b + kc * 8);
-        float4 a1 = *reinterpret_cast<const float4*>(s_b + kc * 8 + 4);
-        if (s_player[bb]) {
-            int cls = (y > 0) + 2 * (y < g - 1) + 4 * ((x > 0) + 2 * (x < g - 1));
-            const float4 p0 = *reinterpret_cast<const float4*>(s_pl + cls * C + kc * 8);
-            const float4 p1 = *reinterpret_cast<const float4*>(s_pl + cls * C + kc * 8 + 4);
-            a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
-            a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
-        }
+    // thread -> (position, chunk phase): lanes of a warp own consecutive positions, so every
+    // 16-byte store of a warp lands in one contiguous run of rows; no per-item divisions.
+    const int pos = threadIdx.x & 63, q = threadIdx.x >> 6;  // blockDim = 256 -> q in 0..3
+    if (pos >= P0) return;
+    const int y = pos / g, x = pos % g;
+    const int cls = (y > 0) + 2 * (y < g - 1) + 4 * ((x > 0) + 2 * (x < g - 1));
+    for (int bb = 0; bb < kEncode2Boards; ++bb) {
+        const int b = b0 + bb;
+        if (b >= live) break;
         const u8* code = s_code + bb * gp * gp;
+        int cd[9];
 #pragma unroll
-        for (int tap = 0; tap < 9; ++tap) {
-            int cd = code[(y + tap / 3) * gp + (x + tap % 3)];
-            if (cd) {
-                const float* wr = s_w + (tap * 3 + cd - 1) * C + kc * 8;
-                const float4 w0 = *reinterpret_cast<const float4*>(wr);
-                const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-                a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
-                a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
+        for (int tap = 0; tap < 9; ++tap) cd[tap] = code[(y + tap / 3) * gp + (x + tap % 3)];
+        const bool first_to_move = s_player[bb] != 0;
+        const size_t row = (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
+        for (int kc = q; kc < chunks; kc += 4) {
+            float4 a0 = *reinterpret_cast<const float4*>(s_b + kc * 8);
+            float4 a1 = *reinterpret_cast<const float4*>(s_b + kc * 8 + 4);
+            if (first_to_move) {
+                const float4 p0 = *reinterpret_cast<const float4*>(s_pl + cls * C + kc * 8);
+                const float4 p1 = *reinterpret_cast<const float4*>(s_pl + cls * C + kc * 8 + 4);
+                a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
+                a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
             }
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                if (cd[tap]) {
+                    const float* wr = s_w + (tap * 3 + cd[tap] - 1) * C + kc * 8;
+                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
+                    const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
+                    a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
+                    a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
+                }
+            }
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f));
+            __nv_bfloat162 q1 = __floats2bfloat162_rn(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f));
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
+            __nv_bfloat162 q3 = __floats2bfloat162_rn(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f));
+            uint4 v;
+            v.x = *reinterpret_cast<u32*>(&q0);
+            v.y = *reinterpret_cast<u32*>(&q1);
+            v.z = *reinterpret_cast<u32*>(&q2);
+            v.w = *reinterpret_cast<u32*>(&q3);
+            *reinterpret_cast<uint4*>(out_bf16 + ((size_t)kc * rows_total + row) * 8) = v;
         }
-        size_t row = (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
-        __nv_bfloat162 q0 = __floats2bfloat162_rn(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f));
-        __nv_bfloat162 q1 = __floats2bfloat162_rn(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f));
-        __nv_bfloat162 q2 = __floats2bfloat162_rn(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
-        __nv_bfloat162 q3 = __floats2bfloat162_rn(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f));
-        uint4 v;
-        v.x = *reinterpret_cast<u32*>(&q0);
-        v.y = *reinterpret_cast<u32*>(&q1);
-        v.z = *reinterpret_cast<u32*>(&q2);
-        v.w = *reinterpret_cast<u32*>(&q3);
-        *reinterpret_cast<uint4*>(out_bf16 + ((size_t)kc * rows_total + row) * 8) = v;
     }
 }
 

@@ -624,8 +624,10 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
 }
 
 // --------------------------------------------------- kernel: external-evaluator select
+// 7 blocks x 4 warps = 28 warps per SM: 148 SMs hold 4144 trees in ONE wave (ncu showed 1.15
+// waves at 80 registers, i.e. a nearly empty second pass over a latency-bound kernel).
 template <bool kSelfPlay>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select(PoolView P) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
     __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
