@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
+    ap.add_argument("--graph", type=int, default=1, help="1 = replay a captured CUDA graph of the round")
     return ap.parse_args()
 
 
@@ -62,7 +63,8 @@ def config_block(args, wl, n_gpus):
                     f"{wl['num_simulations']} sims/move, cutoff {wl['sample_move_cutoff']}, "
                     f"dirichlet {wl['dirichlet_alpha']}",
         "step": f"{wl['num_simulations']} search rounds over the pool (one leaf per tree per round)",
-        "trees_per_gpu": args.trees, "pools_per_gpu": args.pools, "num_simulations": wl["num_simulations"],
+        "trees_per_gpu": args.trees, "pools_per_gpu": args.pools, "cuda_graph": bool(args.graph),
+        "num_simulations": wl["num_simulations"],
         "parallelism": f"games sharded x{n_gpus}",
         "l2_policy": "inputs_larger_than_L2 (per-round activations 2x170 MB + GB-scale tree arenas vs 126 MB L2)",
     }
@@ -113,7 +115,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
-                 "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
             self.proc = None
@@ -165,6 +167,7 @@ def run_b200(args):
     sims, T = wl["num_simulations"], args.trees
     engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
                              replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools)
+    engine.use_graph = bool(args.graph) and args.pools == 1
     dn = net.device_net()   # e2e leg (full-width batches)
     lib = _lib.load()
 
@@ -173,14 +176,12 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also desynchronises the games' phases)
+    # ---- warm-up (also desynchronises the games' phases; captures the round graph when enabled)
     for _ in range(args.warmup):
         engine.run_rounds(sims)
     barrier()
     c0 = engine.counters()
-    launches0 = lib.dm_launch_count()
-    for pdn in engine.device_nets:
-        pdn.profile(True)
+    launches0 = lib.dm_launch_count() + engine.graph_launches()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
@@ -193,14 +194,34 @@ def run_b200(args):
     barrier()
     elapsed_ms = start.elapsed_time(stop)
     clock_info = clocks.stop() if rank == 0 else None
+    launches = lib.dm_launch_count() + engine.graph_launches() - launches0
+    c1 = engine.counters()
+    d = {k: c1[k] - c0[k] for k in c1}
+
+    # ---- per-kernel CUDA-event timing for the roofline.  Events cannot be timed inside a replayed
+    # graph, so the same steps are run once more launch by launch (identical kernels, grids and
+    # data sizes) with an event pair around every network kernel on its launch stream.
+    was_graph = engine.use_graph
+    engine.use_graph = False
+    for pdn in engine.device_nets:
+        pdn.profile(True)
+    p0 = engine.counters()
+    pstart, pstop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_steps = min(args.steps, 3)
+    pstart.record()
+    for _ in range(prof_steps):
+        engine.run_rounds(sims)
+    pstop.record()
+    torch.cuda.synchronize()
+    prof_elapsed_ms = pstart.elapsed_time(pstop)
     prof = {}
     for pdn in engine.device_nets:
         for k, (ms, cnt) in pdn.profile_read().items():
             prof[k] = (prof.get(k, (0.0, 0))[0] + ms, prof.get(k, (0.0, 0))[1] + cnt)
         pdn.profile(False)
-    launches = lib.dm_launch_count() - launches0
-    c1 = engine.counters()
-    d = {k: c1[k] - c0[k] for k in c1}
+    p1 = engine.counters()
+    prof_leaf_evals = p1["leaf_evals"] - p0["leaf_evals"]
+    engine.use_graph = was_graph
 
     # ---- end to end through the public batched API with HOST buffers (pinned), fresh roots per step
     from deep_mcts_b200.pool import TreePool, default_node_capacity
@@ -221,6 +242,17 @@ def run_b200(args):
     d_player = torch.empty(T, dtype=torch.uint8, device="cuda")
     stream = torch.cuda.current_stream().cuda_stream
 
+    e2e_graph = None
+    if args.graph:
+        pool2.begin_step()
+        dn.search_round(pool2)
+        torch.cuda.synchronize()
+        e2e_launches_before = lib.dm_launch_count()
+        e2e_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(e2e_graph):
+            dn.search_round(pool2)
+        e2e_round_launches = int(lib.dm_launch_count() - e2e_launches_before)
+
     def e2e_step():
         d_first.copy_(h_first, non_blocking=True)
         d_second.copy_(h_second, non_blocking=True)
@@ -228,7 +260,11 @@ def run_b200(args):
         _lib.call("dm_pool_set_root_state", pool2._h, 0, T, d_first.data_ptr(), d_second.data_ptr(),
                   d_player.data_ptr(), stream)
         pool2.begin_step()
-        dn.run_search(pool2, sims)
+        if e2e_graph is not None:
+            for _ in range(sims + 1):
+                e2e_graph.replay()
+        else:
+            dn.run_search(pool2, sims)
         _lib.call("dm_pool_root_visits", pool2._h, pool2._visits.data_ptr(), pool2._stats.data_ptr(), stream)
         h_visits.copy_(pool2._visits, non_blocking=True)
         h_stats.copy_(pool2._stats, non_blocking=True)
@@ -268,7 +304,7 @@ def run_b200(args):
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         except Exception:
             pass
-        achieved = (d["leaf_evals"] * 7 * flop_per_leaf_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        achieved = (prof_leaf_evals * 7 * flop_per_leaf_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": tot_sims / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -288,8 +324,10 @@ def run_b200(args):
                 "frac": achieved / peak_tflops if peak_tflops else None, "traffic": None,
                 "peak_source": peak_src, "launches": conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches if conv_launches else None,
-                "algorithmic_flop_per_launch": d["leaf_evals"] * 7 * flop_per_leaf_conv / max(1, conv_launches),
-                "share_of_step": conv_ms / elapsed_ms if elapsed_ms else None,
+                "algorithmic_flop_per_launch": prof_leaf_evals * 7 * flop_per_leaf_conv / max(1, conv_launches),
+                "share_of_step": conv_ms / prof_elapsed_ms if prof_elapsed_ms else None,
+                "timed_in": f"{prof_steps} extra steps launched kernel by kernel right after the timed region "
+                            "(CUDA events cannot be timed inside the replayed graph)",
             },
             "kernel_ms": {k: v[0] for k, v in prof.items()},
             "tree_stats": {"mean_depth": d["depth_sum"] / max(1, d["simulations"]),

@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_policy_fc_tc(FcArgs args) {
 
 // Sums the split-K partial logits, runs the value-head FCs and GameNet.evaluate's
 // post-processing (gamenet.py:67-85).  One warp per board.
-constexpr int kFinishBoards = 8;
+constexpr int kFinishBoards = 16;
 __global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg, int n, const int* count_dev, const u64* first,
                                                       const u64* second, const u8* player,
                                                       const float* __restrict__ partial, int split, int n_cap, int NA,
@@ -698,7 +698,13 @@ __global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg
     const int P0 = cfg.g * cfg.g, A = cfg.num_actions;
     const int live = live_count(count_dev, n);
     if (blockIdx.x * kFinishBoards >= live) return;
-    for (int i = threadIdx.x; i < P0 * hp.H; i += blockDim.x) s_w1[i] = hp.vfc1_t[i];
+    {
+        const int n4 = (P0 * hp.H) >> 2;  // 16-byte staging (P0*H is a multiple of 4 for every supported net)
+        const float4* src = reinterpret_cast<const float4*>(hp.vfc1_t);
+        float4* dst = reinterpret_cast<float4*>(s_w1);
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) dst[i] = __ldg(src + i);
+        for (int i = (n4 << 2) + threadIdx.x; i < P0 * hp.H; i += blockDim.x) s_w1[i] = hp.vfc1_t[i];
+    }
     __syncthreads();
     if (gb >= live) return;
     GState s;

@@ -53,6 +53,10 @@ class BatchedSelfPlay:
         else:
             self._build_device_nets(per_pool)
         self.pool = self.pools[0]
+        self.use_graph = False      # set True to replay one captured round instead of re-launching it
+        self._graph = None
+        self._graph_launches = 0
+        self.graph_replays = 0
         self.streams = [torch.cuda.Stream(device=self.pool.device) for _ in range(n_pools)] if n_pools > 1 else [None]
 
     def _build_device_nets(self, per_pool: int) -> None:
@@ -76,6 +80,13 @@ class BatchedSelfPlay:
         """``rounds`` x (select one leaf per tree -> network batch -> expand + backup) for every pool."""
         if self.n_pools == 1:
             dn, pool = self.device_nets[0], self.pools[0]
+            if self.use_graph:
+                if self._graph is None:
+                    self._capture_round()
+                for _ in range(int(rounds)):
+                    self._graph.replay()
+                self.graph_replays += int(rounds)
+                return
             for _ in range(int(rounds)):
                 dn.search_round(pool, selfplay=True)
             return
@@ -88,6 +99,24 @@ class BatchedSelfPlay:
                     dn.search_round(pool, selfplay=True)
         for st in self.streams:
             current.wait_stream(st)
+
+    def _capture_round(self) -> None:
+        """Capture one select -> network -> expand/backup round (13 kernel launches + 1 memset) into a
+        CUDA graph; the round has no host-visible state, so replaying it is identical to launching it."""
+        dn, pool = self.device_nets[0], self.pools[0]
+        dn.search_round(pool, selfplay=True)        # warm every kernel outside the capture
+        torch.cuda.synchronize()
+        lib = _lib.load()
+        before = lib.dm_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            dn.search_round(pool, selfplay=True)
+        self._graph_launches = int(lib.dm_launch_count() - before)
+        self._graph = graph
+
+    def graph_launches(self) -> int:
+        """Kernel launches executed through graph replays so far."""
+        return self.graph_replays * self._graph_launches
 
     def counters(self) -> dict:
         total = None
