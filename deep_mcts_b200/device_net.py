@@ -120,6 +120,15 @@ class DeviceNet:
                       s.data_ptr(), p.data_ptr(), out.data_ptr(), current_stream())
         return out.cpu().numpy()
 
+    def rollout_greedy_device(self, first: torch.Tensor, second: torch.Tensor, player: torch.Tensor, n: int,
+                              out: torch.Tensor, precision: Optional[str] = None) -> torch.Tensor:
+        """Greedy policy playouts for ``n`` device-resident states into ``out`` (device, float32)."""
+        self._check(n)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_rollout_greedy", self._h, PRECISIONS[precision or self.precision], int(n),
+                      first.data_ptr(), second.data_ptr(), player.data_ptr(), out.data_ptr(), current_stream())
+        return out
+
     # ------------------------------------------------------------------------- profiling
     def profile(self, enable: bool) -> None:
         _lib.call("dm_net_profile", self._h, 1 if enable else 0)

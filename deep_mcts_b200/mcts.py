@@ -63,6 +63,20 @@ def random_rollout_policy(manager: GameManager) -> RolloutPolicy:
     return policy
 
 
+def greedy_policy_rollout(game_net) -> RolloutPolicy:
+    """``lambda state: np.argmax(cached_model(state)[1])`` -- the policy-network rollouts of
+    Experiment 3 (reference evaluate_complex_rollouts.py:57-59).  Given to MCTS it runs as batched
+    device playouts: every ply is one network batch over all pending leaves plus an argmax."""
+    evaluator = game_net.evaluate
+
+    def policy(state):
+        return int(np.argmax(evaluator(state)[1]))
+
+    policy._dm_rollout_kind = "greedy_net"
+    policy._dm_net = game_net
+    return policy
+
+
 def min_action_policy(manager: GameManager) -> RolloutPolicy:
     policy = lambda state: min(manager.legal_actions(state))  # noqa: E731
     policy._dm_rollout_kind = _lib.DM_ROLLOUT_MIN_ACTION
@@ -126,8 +140,16 @@ class BatchedMCTS:
                 self._net = net
             else:
                 self._host_eval = ev
+        self._greedy_net = None
         if ro is None:
             self._rollout_kind = _lib.DM_ROLLOUT_NONE
+        elif getattr(ro, "_dm_rollout_kind", None) == "greedy_net":
+            # device policy-network playouts: leaves go through the exchange path, values are mixed on the device
+            self._rollout_kind = _lib.DM_ROLLOUT_NONE
+            self._greedy_net = ro._dm_net
+            if self._eval_kind not in (_lib.DM_EVAL_NONE, _lib.DM_EVAL_EXTERNAL) or self._host_eval is not None:
+                raise ValueError("policy-network rollouts combine with state_evaluator=None or a GameNet evaluator")
+            self._eval_kind = _lib.DM_EVAL_EXTERNAL
         elif hasattr(ro, "_dm_rollout_kind"):
             self._rollout_kind = ro._dm_rollout_kind
         else:
@@ -177,12 +199,50 @@ class BatchedMCTS:
     def run_simulations(self, sims: int, alpha: Optional[float] = None) -> None:
         self._configure(sims, alpha)
         self.pool.begin_step()
-        if self._eval_kind != _lib.DM_EVAL_EXTERNAL:
+        if self._greedy_net is not None:
+            self._run_greedy_rollout_search(sims)
+        elif self._eval_kind != _lib.DM_EVAL_EXTERNAL:
             self.pool.search_local()
         elif self._net is not None:
             self._net.run_search(self.pool, sims)
         else:
             self.pool.step_external(self._host_evaluate, max_rounds=sims + 2)
+
+    def _run_greedy_rollout_search(self, sims: int) -> None:
+        """select -> (network evaluation | uniform priors) -> greedy policy playouts -> expand/backup.
+        evaluate_leaf's mixing rule with rollout_share = 1 (mcts.py:187-196): the playout value alone
+        without a state evaluator, the mean of playout and network value with one."""
+        pool = self.pool
+        rnet = self._greedy_net.device_net()
+        enet = self._net.device_net() if self._net is not None else None
+        T = pool.n_trees
+        if rnet.max_batch < T or (enet is not None and enet.max_batch < T):
+            raise ValueError("GameNet.max_batch must be >= the number of trees")
+        if not hasattr(self, "_rollout_out"):
+            self._rollout_out = torch.zeros(T, dtype=torch.float32, device=pool.device)
+            self._uniform_value = torch.zeros(T, dtype=torch.float32, device=pool.device)
+            self._uniform_probs = torch.zeros((T, _lib.DM_MAX_ACTIONS), dtype=torch.float32, device=pool.device)
+        stream = torch.cuda.current_stream().cuda_stream
+        for _ in range(int(sims) + 1):
+            pool.select()
+            n = int(pool.leaf_count.item())
+            if n == 0:
+                break
+            if enet is not None:
+                value, probs = enet.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, T,
+                                                    pool.leaf_count)
+                probs = probs.clone()   # the playouts below reuse the network's output buffers
+                value = value.clone()
+            else:
+                with torch.cuda.device(pool.device):
+                    _lib.call("dm_eval_uniform", pool.manager.game_id, pool.manager.board, T,
+                              pool.leaf_count.data_ptr(), pool.leaf_first.data_ptr(), pool.leaf_second.data_ptr(),
+                              pool.leaf_player.data_ptr(), self._uniform_value.data_ptr(),
+                              self._uniform_probs.data_ptr(), stream)
+                value, probs = self._uniform_value, self._uniform_probs
+            rnet.rollout_greedy_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, n, self._rollout_out)
+            mixed = self._rollout_out if enet is None else (self._rollout_out + value) / 2
+            pool.expand_backup(probs, mixed.contiguous())
 
     def step(self) -> Tuple[np.ndarray, np.ndarray]:
         """(visits[n_trees, A], stats[n_trees, 2]) after ``num_simulations`` simulations per tree."""

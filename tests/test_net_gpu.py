@@ -151,3 +151,30 @@ def test_greedy_policy_rollouts_match_oracle():
             s = game.child(s, int(np.argmax(p[0])))
         agree += int(game.outcome(s) == float(out[i]))
     assert agree >= len(states) - 2  # fp32 argmax ties may flip a rare playout
+
+
+def test_mcts_with_policy_network_rollouts_matches_oracle():
+    """Experiment-3 agent (reference evaluate_complex_rollouts.py:53-66): greedy policy-net rollouts,
+    with and without the state evaluator, as batched device playouts vs the oracle's per-state loop."""
+    from deep_mcts_b200.gamenet import cached_state_evaluator
+    from deep_mcts_b200.hex_with_swap.convolutionalnet import ConvolutionalHexWithSwapNet
+    from deep_mcts_b200.mcts import MCTS, greedy_policy_rollout
+    from oracle.mcts import OracleMCTS
+    game = make_game("hex_with_swap", 4)
+    sd = synthetic_state_dict(game, 128, 3, 128, seed=31, conv_gain=1.0, fc_scale=1.0)
+    net = ConvolutionalHexWithSwapNet(4)
+    net.load_state_dict(sd)
+    net.precision = "fp32"
+    oracle_eval = onet.make_evaluator(sd)
+    oracle_rollout = lambda g, s: int(np.argmax(oracle_eval(g, s)[1]))  # noqa: E731
+    for with_evaluator in (False, True):
+        m = MCTS(net.manager, 24, greedy_policy_rollout(net), cached_state_evaluator(net) if with_evaluator else None)
+        ref = OracleMCTS(game, 24, oracle_rollout, oracle_eval if with_evaluator else None)
+        for _ in range(3):
+            dist, stats = m.step()
+            ref_dist, ref_stats = ref.step()
+            assert tuple(stats) == tuple(ref_stats)
+            assert np.abs(np.array(dist) - np.array(ref_dist)).max() <= 2 / 24 + 1e-9
+            a = int(np.argmax(ref_dist))
+            m.advance(a)
+            ref.advance(a)
