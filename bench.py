@@ -50,6 +50,24 @@ def parse_args():
     return ap.parse_args()
 
 
+def ncu_dram_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the trunk conv kernel from the committed
+    `ncu --set full` capture (profiles/), averaged over the captured launches; None if absent."""
+    import csv
+    path = ROOT / "profiles" / "r1c_conv3x3_tc2_ncu_full_raw.csv"
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, data = rows[0], rows[1], rows[2:]
+        total = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(key)
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[units[i]]
+            total += sum(float(r[i]) for r in data) * scale / len(data)
+        return total
+    except Exception:
+        return None
+
+
 def workload_config(args):
     game, grid, sims, cutoff, alpha = WORKLOADS[args.workload]
     return {"game": game, "grid": grid, "num_simulations": sims, "sample_move_cutoff": cutoff,
@@ -321,7 +339,11 @@ def run_b200(args):
             "roofline": {
                 "kernel": "k_conv3x3_tc (tcgen05 implicit-GEMM 3x3 conv, 7 launches per round)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
-                "frac": achieved / peak_tflops if peak_tflops else None, "traffic": None,
+                "frac": achieved / peak_tflops if peak_tflops else None,
+                "traffic": ncu_dram_traffic_per_launch() if wl["game"] == "othello" and args.trees == 4096 else None,
+                "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r1c_conv3x3_tc2_ncu_full_raw.csv)",
+                "algorithmic_bytes_per_launch": args.trees * (wl["grid"] + 1) ** 2 * 256 + args.trees * wl["grid"] ** 2 * 256
+                + 9 * 128 * 128 * 2,
                 "peak_source": peak_src, "launches": conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches if conv_launches else None,
                 "algorithmic_flop_per_launch": prof_leaf_evals * 7 * flop_per_leaf_conv / max(1, conv_launches),

@@ -231,8 +231,8 @@ class BatchedMCTS:
             if enet is not None:
                 value, probs = enet.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, T,
                                                     pool.leaf_count)
-                probs = probs.clone()   # the playouts below reuse the network's output buffers
-                value = value.clone()
+                probs = probs[:T].clone()   # the playouts below reuse the network's output buffers
+                value = value[:T].clone()
             else:
                 with torch.cuda.device(pool.device):
                     _lib.call("dm_eval_uniform", pool.manager.game_id, pool.manager.board, T,
