@@ -11,6 +11,7 @@ from pathlib import Path
 
 DM_MAX_ACTIONS = 65
 DM_MAX_DEPTH = 128
+DM_MAX_LEAVES = 8
 
 DM_TICTACTOE, DM_HEX, DM_HEX_SWAP, DM_OTHELLO = 0, 1, 2, 3
 DM_EVAL_NONE, DM_EVAL_UNIFORM, DM_EVAL_HASHED, DM_EVAL_EXTERNAL = 0, 1, 2, 3
@@ -32,7 +33,7 @@ class SearchConfig(ctypes.Structure):
     _fields_ = [
         ("num_simulations", c_int32), ("eval_kind", c_int32), ("rollout_kind", c_int32),
         ("sample_move_cutoff", c_int32), ("dirichlet_alpha", c_double), ("dirichlet_factor", c_double),
-        ("rollout_share", c_double), ("eval_salt", c_uint64),
+        ("rollout_share", c_double), ("eval_salt", c_uint64), ("leaves_per_round", c_int32), ("reserved1", c_int32),
     ]
 
 

@@ -41,6 +41,7 @@ struct PoolView {
     int num_simulations, eval_kind, rollout_kind, sample_move_cutoff;
     double dirichlet_alpha, dirichlet_factor, rollout_share;
     u64 eval_salt;
+    int leaves_per_round;      // 1 = exact; > 1 = virtual-loss mode
     const double* host_noise;  // [n_trees][DM_MAX_ACTIONS] in child order, or null
     // nodes
     u32* visits;
@@ -70,6 +71,12 @@ struct PoolView {
     u8* leaf_flags;
     int* leaf_tree;
     int* leaf_count;
+    // virtual-loss mode: up to DM_MAX_LEAVES pending paths per tree
+    u32* vl_path;   // [n_trees][DM_MAX_LEAVES][DM_MAX_DEPTH]
+    int* vl_len;    // [n_trees][DM_MAX_LEAVES]
+    int* vl_slot;   // [n_trees][DM_MAX_LEAVES] leaf-batch slot of each pending path
+    int* vl_count;  // [n_trees]
+    int* armed;     // number of trees that still have simulations left after the last select
     unsigned long long* counters;
     // self-play recording
     int selfplay;
@@ -773,6 +780,174 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
 }
 
+// ---------------------------------------------------------------- virtual-loss mode
+// Throughput mode for small pools: a tree hands out up to leaves_per_round leaves per round.
+// After each descent the path gets a virtual loss -- one extra visit scored as a loss for the
+// player who chose the node (the same value the reference gives an unvisited child,
+// mcts.py:48-50) -- so the next descent of the same round explores elsewhere.  A leaf that is
+// already pending is marked (first_child = kPendingLeaf); reaching it again ends the round for
+// that tree.  k_expand_backup_vl removes the virtual losses while backing up the real values.
+// Not bit-identical to the reference (simulations are reordered); W = 1 uses the exact kernels.
+constexpr u32 kPendingLeaf = 0xffffffffu;
+
+__device__ __forceinline__ double loss_value_for_parent(int root_player, int depth_of_child) {
+    // the node at depth d was chosen by the player to move at depth d-1; every action flips the mover
+    int parent_player = root_player ^ ((depth_of_child - 1) & 1);
+    return parent_player == 1 ? 1.0 : 0.0;  // FIRST (min player) loses at 1.0, SECOND at 0.0
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_vl(PoolView P) {
+    __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    u32* path = s_path[warp];
+    const int W = P.leaves_per_round;
+    unsigned long long scanned = 0, depth = 0, terminal = 0, done = 0;
+    int sims = P.sims_left[t];
+    u8 flags = P.flags[t];
+    u32 without = P.stat_without[t];
+    const int root_player = P.root_player[t];
+    int pending = 0;
+    while (pending < W && pending < sims) {
+        u32 root = P.root[t];
+        GState s;
+        int len;
+        u8 leaf_flag = 0;
+        if (P.n_children[base + root] == 0) {
+            if (pending > 0) break;
+            s = root_state(P, t);
+            if (lane == 0) path[0] = root;
+            len = 1;
+            leaf_flag = kLeafRoot;
+            __syncwarp();
+        } else {
+            if (flags & kFlagNeedNoise) {
+                apply_root_noise(P, t, lane);
+                flags &= ~kFlagNeedNoise;
+            }
+            bool overflow;
+            len = descend(P, t, lane, s, path, scanned, overflow);
+            if (overflow) {
+                if (lane == 0) count(P, kCntCapacity, 1);
+                sims = 0;
+                break;
+            }
+            u32 leaf = path[len - 1];
+            if (P.first_child[base + leaf] == kPendingLeaf) break;  // collision with a leaf of this round
+            depth += (unsigned long long)(len - 1);
+            float outcome;
+            if (game_is_final(P.cfg, s, outcome)) {
+                backup(P, t, lane, path, len, (double)outcome);
+                ++without;
+                ++terminal;
+                ++done;
+                --sims;
+                continue;
+            }
+            // virtual loss along the path, mark the leaf
+            for (int i = lane; i < len; i += 32) {
+                size_t idx = base + path[i];
+                P.visits[idx] += 1;
+                if (i > 0) P.value_sum[idx] = __dadd_rn(P.value_sum[idx], loss_value_for_parent(root_player, i));
+            }
+            if (lane == 0) P.first_child[base + leaf] = kPendingLeaf;
+            __syncwarp();
+        }
+        int slot = 0;
+        if (lane == 0) slot = atomicAdd(P.leaf_count, 1);
+        slot = __shfl_sync(DM_FULL_MASK, slot, 0);
+        u32* dst = P.vl_path + ((size_t)t * DM_MAX_LEAVES + pending) * DM_MAX_DEPTH;
+        for (int i = lane; i < len; i += 32) dst[i] = path[i];
+        if (lane == 0) {
+            P.vl_len[t * DM_MAX_LEAVES + pending] = len;
+            P.vl_slot[t * DM_MAX_LEAVES + pending] = slot;
+            P.leaf_first[slot] = s.first;
+            P.leaf_second[slot] = s.second;
+            P.leaf_player[slot] = (u8)s.player;
+            P.leaf_flags[slot] = leaf_flag;
+            P.leaf_tree[slot] = t;
+        }
+        ++pending;
+        if (leaf_flag & kLeafRoot) break;
+        __syncwarp();
+    }
+    if (lane == 0) {
+        P.sims_left[t] = sims;
+        P.stat_without[t] = without;
+        P.flags[t] = flags;
+        P.vl_count[t] = pending;
+        if (sims > 0) atomicAdd(P.armed, 1);
+        count(P, kCntSims, done);
+        count(P, kCntTerminal, terminal);
+        count(P, kCntDepth, depth);
+        count(P, kCntScanned, scanned);
+    }
+}
+
+template <typename PriorT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_expand_backup_vl(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
+    __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    const int pending = P.vl_count[t];
+    const int root_player = P.root_player[t];
+    int completed = 0;
+    for (int w = 0; w < pending; ++w) {
+        const int slot = P.vl_slot[t * DM_MAX_LEAVES + w];
+        const int len = P.vl_len[t * DM_MAX_LEAVES + w];
+        const u32* path = P.vl_path + ((size_t)t * DM_MAX_LEAVES + w) * DM_MAX_DEPTH;
+        GState s;
+        s.first = P.leaf_first[slot];
+        s.second = P.leaf_second[slot];
+        s.player = P.leaf_player[slot];
+        const u8 leaf_flag = P.leaf_flags[slot];
+        const u32 leaf = path[len - 1];
+        if (lane == 0 && !(leaf_flag & kLeafRoot)) P.first_child[base + leaf] = 0;  // clear the pending mark
+        __syncwarp();
+        double ev;
+        const PriorT* pr = priors + (size_t)slot * stride;
+        bool ok;
+        if (sizeof(PriorT) == 8) ok = expand(P, t, lane, leaf, s, s_order[warp], DM_EVAL_EXTERNAL, nullptr,
+                                             (const double*)pr, ev);
+        else ok = expand(P, t, lane, leaf, s, s_order[warp], DM_EVAL_EXTERNAL, (const float*)pr, nullptr, ev);
+        if (!ok) {
+            if (lane == 0) P.sims_left[t] = 0;
+            break;
+        }
+        if (leaf_flag & kLeafRoot) {
+            if (lane == 0) P.visits[base + path[0]] += 1;
+            __syncwarp();
+            u8 flags = P.flags[t];
+            if (flags & kFlagNeedNoise) {
+                apply_root_noise(P, t, lane);
+                if (lane == 0) P.flags[t] = flags & ~kFlagNeedNoise;
+            }
+        } else {
+            const double value = (double)values[slot];
+            // the visit was already counted by the virtual loss; swap the loss for the real value
+            for (int i = lane; i < len; i += 32) {
+                size_t idx = base + path[i];
+                double delta = (i > 0) ? __dsub_rn(value, loss_value_for_parent(root_player, i)) : value;
+                P.value_sum[idx] = __dadd_rn(P.value_sum[idx], delta);
+            }
+            __syncwarp();
+            ++completed;
+        }
+    }
+    if (lane == 0) {
+        P.sims_left[t] -= completed;
+        P.stat_with[t] += (u32)completed;
+        P.vl_count[t] = 0;
+        count(P, kCntSims, (unsigned long long)completed);
+        count(P, kCntLeafEvals, (unsigned long long)pending);
+    }
+}
+
 // ------------------------------------------------------------------- kernels: read-out
 __global__ void k_root_visits(PoolView P, u32* visits_out, u32* stats_out) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -932,9 +1107,11 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
         (rc = pool_alloc(p, &v.stat_with, T)) || (rc = pool_alloc(p, &v.stat_without, T)) ||
         (rc = pool_alloc(p, &v.flags, T)) || (rc = pool_alloc(p, &v.ply, T)) ||
         (rc = pool_alloc(p, &v.rng_ctr, T)) || (rc = pool_alloc(p, &v.path, T * DM_MAX_DEPTH)) ||
-        (rc = pool_alloc(p, &v.path_len, T)) || (rc = pool_alloc(p, &v.leaf_first, T)) ||
-        (rc = pool_alloc(p, &v.leaf_second, T)) || (rc = pool_alloc(p, &v.leaf_player, T)) ||
-        (rc = pool_alloc(p, &v.leaf_flags, T)) || (rc = pool_alloc(p, &v.leaf_tree, T)) ||
+        (rc = pool_alloc(p, &v.path_len, T)) || (rc = pool_alloc(p, &v.leaf_first, T * DM_MAX_LEAVES)) ||
+        (rc = pool_alloc(p, &v.leaf_second, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.leaf_player, T * DM_MAX_LEAVES)) ||
+        (rc = pool_alloc(p, &v.leaf_flags, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.leaf_tree, T * DM_MAX_LEAVES)) ||
+        (rc = pool_alloc(p, &v.vl_len, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.vl_slot, T * DM_MAX_LEAVES)) ||
+        (rc = pool_alloc(p, &v.vl_count, T)) || (rc = pool_alloc(p, &v.armed, 1)) ||
         (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)))
         return fail(rc);
     k_reset<<<(cfg->n_trees + 127) / 128, 128>>>(v, nullptr, cfg->n_trees);
@@ -974,6 +1151,13 @@ extern "C" int dm_pool_configure(dm_pool* p, const dm_search_config* sc) {
     v.dirichlet_factor = sc->dirichlet_factor;
     v.rollout_share = sc->rollout_share;
     v.eval_salt = sc->eval_salt;
+    DM_CHECK_ARG(sc->leaves_per_round >= 0 && sc->leaves_per_round <= DM_MAX_LEAVES,
+                 "dm_pool_configure: leaves_per_round out of range");
+    v.leaves_per_round = sc->leaves_per_round > 1 ? sc->leaves_per_round : 1;
+    if (v.leaves_per_round > 1 && !v.vl_path) {
+        DM_CUDA(cudaSetDevice(p->cfg.device));
+        DM_TRY(pool_alloc(p, &v.vl_path, (size_t)v.n_trees * DM_MAX_LEAVES * DM_MAX_DEPTH, false));
+    }
     p->configured = true;
     return DM_OK;
 }
@@ -1044,6 +1228,16 @@ static int launch_select(dm_pool* p, void* stream, bool selfplay) {
         return DM_ERR_STATE;
     }
     DM_CUDA(cudaMemsetAsync(p->v.leaf_count, 0, sizeof(int), (cudaStream_t)stream));
+    if (p->v.leaves_per_round > 1) {
+        if (selfplay) {
+            dm_set_error("virtual-loss mode is not available for continuous self-play (use leaves_per_round = 1)");
+            return DM_ERR_STATE;
+        }
+        DM_CUDA(cudaMemsetAsync(p->v.armed, 0, sizeof(int), (cudaStream_t)stream));
+        k_select_vl<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v);
+        DM_LAUNCH_CHECK();
+        return DM_OK;
+    }
     if (selfplay)
         k_select<true><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v);
     else
@@ -1072,6 +1266,16 @@ extern "C" int dm_pool_expand_backup(dm_pool* p, const void* priors, int stride,
                                      void* stream) {
     DM_CHECK_ARG(p && priors && values, "dm_pool_expand_backup: null argument");
     DM_CHECK_ARG(stride >= p->v.cfg.num_actions, "dm_pool_expand_backup: prior_stride < num_actions");
+    if (p->v.leaves_per_round > 1) {
+        if (is_f64)
+            k_expand_backup_vl<double><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+                p->v, (const double*)priors, stride, (const double*)values);
+        else
+            k_expand_backup_vl<float><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+                p->v, (const float*)priors, stride, (const float*)values);
+        DM_LAUNCH_CHECK();
+        return DM_OK;
+    }
     if (is_f64)
         k_expand_backup<double><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             p->v, (const double*)priors, stride, (const double*)values);

@@ -147,11 +147,18 @@ class DeviceNet:
             pool.selfplay_select()
         else:
             pool.select()
-        value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.n_trees,
+        value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity,
                                             pool.leaf_count)
         pool.expand_backup(probs, value)
 
     def run_search(self, pool, sims: int) -> None:
-        """All armed simulations of one MCTS.step: at most sims + 1 rounds (root expansion)."""
-        for _ in range(int(sims) + 1):
+        """All armed simulations of one MCTS.step.  Exact mode: at most sims + 1 rounds (root
+        expansion), no host synchronisation.  Virtual-loss mode: rounds until no tree hands out a leaf."""
+        if pool.leaves_per_round == 1:
+            for _ in range(int(sims) + 1):
+                self.search_round(pool)
+            return
+        for _ in range(int(sims) + 2):
             self.search_round(pool)
+            if int(pool.leaf_count.item()) == 0:
+                break

@@ -107,9 +107,11 @@ class BatchedMCTS:
     def __init__(self, game_manager: BoardManager, n_trees: int, num_simulations: int,
                  rollout_policy: Optional[RolloutPolicy], state_evaluator: Optional[StateEvaluator],
                  sample_move_cutoff: int = 0, dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25,
-                 rollout_share: float = 1.0, max_nodes_per_tree: Optional[int] = None, seed: int = 0) -> None:
+                 rollout_share: float = 1.0, max_nodes_per_tree: Optional[int] = None, seed: int = 0,
+                 leaves_per_round: int = 1) -> None:
         if rollout_policy is None and state_evaluator is None:
             raise ValueError("Both rollout_policy and state_evaluator cannot be None")
+        self.leaves_per_round = int(leaves_per_round)
         self.game_manager = game_manager
         self.num_simulations = num_simulations
         self.rollout_policy = rollout_policy
@@ -161,9 +163,10 @@ class BatchedMCTS:
                 self._eval_kind = _lib.DM_EVAL_EXTERNAL
 
     def _configure(self, sims: int, alpha: Optional[float] = None) -> None:
+        vl = self.leaves_per_round if self._eval_kind == _lib.DM_EVAL_EXTERNAL and self._greedy_net is None else 1
         self.pool.configure(sims, self._eval_kind, self._rollout_kind, self.sample_move_cutoff,
                             self.dirichlet_alpha if alpha is None else alpha, self.dirichlet_factor,
-                            self.rollout_share, self._salt)
+                            self.rollout_share, self._salt, vl)
 
     # ---- host leaf exchange -----------------------------------------------------------
     def _host_evaluate(self, player, first, second):
@@ -265,9 +268,9 @@ class MCTS(BatchedMCTS):
                  state_evaluator: Optional[StateEvaluator], sample_move_cutoff: int = 0,
                  dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, rollout_share: float = 1.0,
                  time_per_move: float = float("inf"), max_nodes_per_tree: Optional[int] = None,
-                 seed: int = 0) -> None:
+                 seed: int = 0, leaves_per_round: int = 1) -> None:
         super().__init__(game_manager, 1, num_simulations, rollout_policy, state_evaluator, sample_move_cutoff,
-                         dirichlet_alpha, dirichlet_factor, rollout_share, max_nodes_per_tree, seed)
+                         dirichlet_alpha, dirichlet_factor, rollout_share, max_nodes_per_tree, seed, leaves_per_round)
         self.time_per_move = time_per_move
         self.state = game_manager.initial_game_state()
 

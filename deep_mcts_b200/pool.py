@@ -55,10 +55,12 @@ class TreePool:
         ptrs = [_lib.c_void_p() for _ in range(5)]
         _lib.call("dm_pool_leaf_buffers", self._h, *ptrs)
         T = self.n_trees
-        self.leaf_first = wrap_device_buffer(ptrs[0].value, (T,), torch.int64, self.device)
-        self.leaf_second = wrap_device_buffer(ptrs[1].value, (T,), torch.int64, self.device)
-        self.leaf_player = wrap_device_buffer(ptrs[2].value, (T,), torch.uint8, self.device)
-        self.leaf_tree = wrap_device_buffer(ptrs[3].value, (T,), torch.int32, self.device)
+        cap = T * _lib.DM_MAX_LEAVES   # leaf-batch capacity (virtual-loss mode hands out several leaves per tree)
+        self.leaves_per_round = 1
+        self.leaf_first = wrap_device_buffer(ptrs[0].value, (cap,), torch.int64, self.device)
+        self.leaf_second = wrap_device_buffer(ptrs[1].value, (cap,), torch.int64, self.device)
+        self.leaf_player = wrap_device_buffer(ptrs[2].value, (cap,), torch.uint8, self.device)
+        self.leaf_tree = wrap_device_buffer(ptrs[3].value, (cap,), torch.int32, self.device)
         self.leaf_count = wrap_device_buffer(ptrs[4].value, (1,), torch.int32, self.device)
         self._visits = torch.zeros((T, _lib.DM_MAX_ACTIONS), dtype=torch.int32, device=self.device)
         self._stats = torch.zeros((T, 2), dtype=torch.int32, device=self.device)
@@ -78,12 +80,20 @@ class TreePool:
     def configure(self, num_simulations: int, eval_kind: int = _lib.DM_EVAL_EXTERNAL,
                   rollout_kind: int = _lib.DM_ROLLOUT_NONE, sample_move_cutoff: int = 0,
                   dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, rollout_share: float = 1.0,
-                  eval_salt: int = 0) -> None:
+                  eval_salt: int = 0, leaves_per_round: int = 1) -> None:
+        """``leaves_per_round`` = 1 is the exact mode (bit-identical visit counts); 2..8 hands out that
+        many leaves per tree per round with virtual loss (throughput mode for small pools)."""
         sc = _lib.SearchConfig(int(num_simulations), int(eval_kind), int(rollout_kind), int(sample_move_cutoff),
                                float(dirichlet_alpha), float(dirichlet_factor), float(rollout_share),
-                               int(eval_salt))
+                               int(eval_salt), int(leaves_per_round), 0)
         _lib.call("dm_pool_configure", self._h, sc)
         self._search = sc
+        self.leaves_per_round = max(1, int(leaves_per_round))
+
+    @property
+    def leaf_capacity(self) -> int:
+        """Largest number of leaves one select can hand out with the current configuration."""
+        return self.n_trees * self.leaves_per_round
 
     def _ids(self, tree_ids):
         if tree_ids is None:
@@ -172,9 +182,9 @@ class TreePool:
             f = self.leaf_first[:n].cpu().numpy().view(np.uint64)
             s = self.leaf_second[:n].cpu().numpy().view(np.uint64)
             values, priors = evaluate(p, f, s)
-            pri = np.zeros((self.n_trees, _lib.DM_MAX_ACTIONS), dtype=np.float64)
+            pri = np.zeros((self.leaf_capacity, _lib.DM_MAX_ACTIONS), dtype=np.float64)
             pri[:n, : self.num_actions] = np.asarray(priors, dtype=np.float64)[:, : self.num_actions]
-            val = np.zeros(self.n_trees, dtype=np.float64)
+            val = np.zeros(self.leaf_capacity, dtype=np.float64)
             val[:n] = np.asarray(values, dtype=np.float64)
             self.expand_backup(torch.from_numpy(pri).to(self.device), torch.from_numpy(val).to(self.device))
             rounds += 1

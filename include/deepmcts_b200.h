@@ -42,6 +42,7 @@ extern "C" {
 #define DM_ABI_VERSION 1
 #define DM_MAX_ACTIONS 65   /* 8x8 board + pass/swap */
 #define DM_MAX_DEPTH 128    /* longest root-to-leaf path / plies per game recorded */
+#define DM_MAX_LEAVES 8     /* leaves one tree may have in flight per round (virtual-loss mode) */
 
 typedef enum {
     DM_OK = 0,
@@ -87,6 +88,13 @@ typedef struct {
     double dirichlet_factor;
     double rollout_share;
     uint64_t eval_salt;          /* DM_EVAL_HASHED only */
+    /* 1 (default, 0 means 1) = exact mode: one simulation in flight per tree, visit counts
+     * bit-identical to the reference.  2..DM_MAX_LEAVES = throughput mode for small pools
+     * (tournaments, single-game play): each dm_pool_select hands out up to that many leaves per
+     * tree, steering later descents away from earlier ones with a virtual loss (one extra visit
+     * scored as a loss for the player who chose the node) that dm_pool_expand_backup removes. */
+    int32_t leaves_per_round;
+    int32_t reserved1;
 } dm_search_config;
 
 typedef struct dm_pool dm_pool;
@@ -156,7 +164,8 @@ int dm_pool_search_local(dm_pool* pool, void* stream);
  * every armed tree runs simulations until one reaches a non-final leaf; those leaves are
  * written compactly to the pool's leaf buffers. */
 int dm_pool_select(dm_pool* pool, void* stream);
-/* device buffers filled by dm_pool_select: states of the pending leaves and their count */
+/* device buffers filled by dm_pool_select: states of the pending leaves and their count
+ * (capacity n_trees * DM_MAX_LEAVES entries) */
 int dm_pool_leaf_buffers(dm_pool* pool, uint64_t** first_dev, uint64_t** second_dev, uint8_t** player_dev,
                          int32_t** tree_dev, int32_t** count_dev);
 /* phase 2 (expand_node + rollout mix + backpropagate, mcts.py:186-231): values_dev[slot]

@@ -184,3 +184,79 @@ def test_device_dirichlet_and_random_rollouts_run():
                  rollout_share=0.5)
     dist, stats = m2.step()
     assert sum(stats) == 32
+
+
+@pytest.mark.parametrize("name,g,W", [("othello", 8, 4), ("hex", 7, 3), ("hex_with_swap", 5, 2)])
+def test_virtual_loss_mode_invariants_and_quality(name, g, W):
+    """Throughput mode (several leaves per tree per round, virtual loss): not bit-exact by design,
+    but every simulation must be accounted for and the visit distribution must stay close to the
+    exact search (the synthetic evaluator is pure noise, so only a loose similarity is meaningful)."""
+    from deep_mcts_b200._engine import state_to_bits
+    from deep_mcts_b200 import mcts as dm
+    game = make_game(name, g)
+    manager = manager_for(name, g)
+    sims, T = 96, 48
+    ev = lambda state: oev.hashed(game, state_to_bits(state))  # noqa: E731  host evaluator -> leaf exchange
+    exact = dm.BatchedMCTS(manager, T, sims, None, ev)
+    fast = dm.BatchedMCTS(manager, T, sims, None, ev, leaves_per_round=W)
+    # distinct openings per tree
+    rs = np.random.RandomState(1)
+    p, f, s = manager.initial_batch(T)
+    for _ in range(3):
+        lst, _, cnt = manager.legal_batch(p, f, s)
+        acts = np.array([lst[i, rs.randint(cnt[i])] for i in range(T)], np.int32)
+        p, f, s, ok = manager.child_batch(p, f, s, acts)
+        assert ok.all()
+    exact.pool.set_root_states(p, f, s)
+    fast.pool.set_root_states(p, f, s)
+    agree, l1 = [], []
+    for ply in range(3):
+        v_exact, s_exact = exact.step()
+        v_fast, s_fast = fast.step()
+        assert (s_fast.sum(axis=1) == sims).all() and (s_exact.sum(axis=1) == sims).all()
+        assert (v_fast.sum(axis=1) >= sims - 1).all()
+        pe = v_exact / v_exact.sum(axis=1, keepdims=True)
+        pf = v_fast / v_fast.sum(axis=1, keepdims=True)
+        agree.append((pe.argmax(axis=1) == pf.argmax(axis=1)).mean())
+        l1.append(np.abs(pe - pf).sum(axis=1).mean())
+        actions = np.array([int(np.argmax(v_exact[t])) for t in range(T)], np.int32)
+        exact.advance(actions)
+        fast.advance(actions)
+    assert np.mean(agree) > 0.3, (agree, l1)
+    assert np.mean(l1) < 1.3, (agree, l1)
+    assert fast.pool.counters()["capacity_errors"] == 0
+
+
+def test_virtual_loss_finds_forced_win():
+    """Tic-tac-toe, FIRST to move with two in a row: both modes must put most visits on the winning cell."""
+    from deep_mcts_b200 import mcts as dm
+    from deep_mcts_b200._engine import state_to_bits
+    game = make_game("tictactoe", 3)
+    manager = manager_for("tictactoe", 3)
+    # X X .      FIRST = X to move, wins at cell 2
+    # O O .
+    # . . .
+    state = (1, 0b000000011, 0b000011000)
+    ev = lambda st: oev.uniform(game, state_to_bits(st))  # noqa: E731
+    for W in (1, 4):
+        m = dm.MCTS(manager, 200, None, ev, leaves_per_round=W)
+        m.pool.set_root_states([state[0]], [state[1]], [state[2]])
+        m.state = manager._make_state(*state)
+        dist, stats = m.step()
+        assert int(np.argmax(dist)) == 2 and dist[2] > 0.5, (W, dist)
+
+
+def test_virtual_loss_values_are_restored():
+    """After a virtual-loss step no node may keep a virtual loss: root children means stay in [0, 1]
+    and the visit total equals the simulations run (checked through a second exact step on the same tree)."""
+    from deep_mcts_b200 import mcts as dm
+    from deep_mcts_b200._engine import state_to_bits
+    game = make_game("othello", 6)
+    manager = manager_for("othello", 6)
+    ev = lambda state: oev.hashed(game, state_to_bits(state))  # noqa: E731
+    m = dm.MCTS(manager, 64, None, ev, leaves_per_round=4)
+    dist, stats = m.step()
+    assert sum(stats) == 64 and abs(sum(dist) - 1) < 1e-12
+    root = m.root
+    assert sum(c.visits for c in root.children.values()) == 64
+    assert root.visits == 65
