@@ -260,3 +260,48 @@ def test_virtual_loss_values_are_restored():
     root = m.root
     assert sum(c.visits for c in root.children.values()) == 64
     assert root.visits == 65
+
+
+def test_full_size_pool_consistency_and_oracle_subset():
+    """BASELINE size (4096 Othello 8x8 trees, 50 sims): 8 distinct openings x 512 copies.  Copies of
+    one opening run in different warps / blocks / SMs and must produce identical results (checksum
+    of checksums); one tree per opening is compared with the oracle bit for bit; totals must add up."""
+    from deep_mcts_b200 import mcts as dm
+    game = make_game("othello", 8)
+    manager = manager_for("othello", 8)
+    T, K, sims = 4096, 8, 50
+    rs = np.random.RandomState(7)
+    openings = []
+    for _ in range(K):
+        s = game.initial_state()
+        for _ in range(4):
+            legal = game.legal_list(s)
+            s = game.child(s, legal[rs.randint(len(legal))])
+        openings.append(s)
+    idx = np.arange(T) % K
+    p = np.array([openings[i][0] for i in idx], np.uint8)
+    f = np.array([openings[i][1] for i in idx], np.uint64)
+    s2 = np.array([openings[i][2] for i in idx], np.uint64)
+    batch = dm.BatchedMCTS(manager, T, sims, None, dm.hashed_state_evaluator(manager, 3))
+    batch.pool.set_root_states(p, f, s2)
+    refs = []
+    for o in openings:
+        r = OracleMCTS(game, sims, None, oev.hashed_salted(3))
+        r.set_root_state(o)
+        refs.append(r)
+    c_before = batch.pool.counters()
+    for move in range(4):
+        visits, stats = batch.step()
+        assert (stats.sum(axis=1) == sims).all()
+        for k in range(K):
+            group = visits[idx == k]
+            assert (group == group[0]).all(), f"copies of opening {k} diverged at move {move}"
+            _, ref_stats = refs[k].step()
+            assert [int(v) for v in group[0]] == refs[k].root_visit_counts()
+            assert tuple(stats[k]) == tuple(ref_stats)
+        actions = np.array([int(np.argmax(visits[t])) for t in range(T)], np.int32)
+        for k in range(K):
+            refs[k].advance(int(actions[k]))
+        batch.advance(actions)
+    c = batch.pool.counters()
+    assert c["simulations"] - c_before["simulations"] == T * sims * 4 and c["capacity_errors"] == 0
