@@ -70,6 +70,7 @@ _SIGNATURES = {
     "dm_pool_set_root_state": (c_int, [_P, _P, c_int, _P, _P, _P, _P]),
     "dm_pool_observe": (c_int, [_P, _P, c_int, _P, _P, _P, _P]),
     "dm_pool_begin_step": (c_int, [_P, _P]),
+    "dm_pool_begin_step_ids": (c_int, [_P, _P, c_int, _P]),
     "dm_pool_set_noise": (c_int, [_P, _P]),
     "dm_pool_search_local": (c_int, [_P, _P]),
     "dm_pool_select": (c_int, [_P, _P]),

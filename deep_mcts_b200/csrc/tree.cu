@@ -420,6 +420,23 @@ __global__ void k_begin_step(PoolView P) {
     arm_step(P, t);
 }
 
+// arm only the listed trees; every other tree is parked (sims_left = 0) for this step
+__global__ void k_begin_step_ids(PoolView P, const int* ids, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < P.n_trees) {
+        P.sims_left[i] = 0;
+        P.stat_with[i] = 0;
+        P.stat_without[i] = 0;
+        P.flags[i] &= ~(kFlagNeedNoise | kFlagStepActive);
+    }
+}
+__global__ void k_arm_ids(PoolView P, const int* ids, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int t = ids[i];
+    if (t >= 0 && t < P.n_trees) arm_step(P, t);
+}
+
 // ------------------------------------------------------- kernel: whole search in one launch
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search_local(PoolView P) {
     __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
@@ -1202,6 +1219,21 @@ extern "C" int dm_pool_begin_step(dm_pool* p, void* stream) {
     }
     k_begin_step<<<(p->v.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v);
     DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_begin_step_ids(dm_pool* p, const int32_t* ids, int n, void* stream) {
+    DM_CHECK_ARG(p && n >= 0 && (ids || n == 0), "dm_pool_begin_step_ids: bad arguments");
+    if (!p->configured) {
+        dm_set_error("dm_pool_begin_step_ids: dm_pool_configure has not been called");
+        return DM_ERR_STATE;
+    }
+    k_begin_step_ids<<<(p->v.n_trees + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v, ids, n);
+    DM_LAUNCH_CHECK();
+    if (n > 0) {
+        k_arm_ids<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p->v, ids, n);
+        DM_LAUNCH_CHECK();
+    }
     return DM_OK;
 }
 

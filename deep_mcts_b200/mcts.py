@@ -199,9 +199,9 @@ class BatchedMCTS:
         return m.evaluate_final_state(state).value
 
     # ---- one MCTS.step for every tree -------------------------------------------------
-    def run_simulations(self, sims: int, alpha: Optional[float] = None) -> None:
+    def run_simulations(self, sims: int, alpha: Optional[float] = None, tree_ids=None) -> None:
         self._configure(sims, alpha)
-        self.pool.begin_step()
+        self.pool.begin_step(tree_ids)
         if self._greedy_net is not None:
             self._run_greedy_rollout_search(sims)
         elif self._eval_kind != _lib.DM_EVAL_EXTERNAL:
@@ -247,9 +247,10 @@ class BatchedMCTS:
             mixed = self._rollout_out if enet is None else (self._rollout_out + value) / 2
             pool.expand_backup(probs, mixed.contiguous())
 
-    def step(self) -> Tuple[np.ndarray, np.ndarray]:
-        """(visits[n_trees, A], stats[n_trees, 2]) after ``num_simulations`` simulations per tree."""
-        self.run_simulations(int(self.num_simulations))
+    def step(self, tree_ids=None) -> Tuple[np.ndarray, np.ndarray]:
+        """(visits[n_trees, A], stats[n_trees, 2]) after ``num_simulations`` simulations per tree
+        (only on ``tree_ids`` when given; the other trees are left untouched)."""
+        self.run_simulations(int(self.num_simulations), tree_ids=tree_ids)
         visits, stats = self.pool.root_visits()
         self.pool.counters()  # surfaces capacity errors
         return visits, stats

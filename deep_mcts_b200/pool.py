@@ -144,9 +144,14 @@ class TreePool:
         _lib.call("dm_pool_set_noise", self._h, self._noise.data_ptr())
 
     # --------------------------------------------------------------------------- search
-    def begin_step(self) -> None:
+    def begin_step(self, tree_ids=None) -> None:
+        """Arm one MCTS.step on every tree, or only on ``tree_ids`` (the others sit the step out)."""
         with torch.cuda.device(self.device):
-            _lib.call("dm_pool_begin_step", self._h, self._stream())
+            if tree_ids is None:
+                _lib.call("dm_pool_begin_step", self._h, self._stream())
+            else:
+                ids, n, ptr = self._ids(tree_ids)
+                _lib.call("dm_pool_begin_step_ids", self._h, ptr, n, self._stream())
 
     def search_local(self) -> None:
         with torch.cuda.device(self.device):

@@ -154,6 +154,9 @@ int dm_pool_observe(dm_pool* pool, const int32_t* tree_ids_dev, int n, const uin
  * final, clear the per-step stats.  Root expansion and Dirichlet noise happen inside the
  * search calls below. */
 int dm_pool_begin_step(dm_pool* pool, void* stream);
+/* the same for the listed trees only; all other trees sit this step out (batched tournaments:
+ * an MCTSAgent searches only when it is its turn, tournament.py:97-108) */
+int dm_pool_begin_step_ids(dm_pool* pool, const int32_t* tree_ids_dev, int n, void* stream);
 /* host-supplied Dirichlet noise for the next root-noise application, noise_dev[n_trees][DM_MAX_ACTIONS]
  * in child order (parity tests; NULL = sample on device) */
 int dm_pool_set_noise(dm_pool* pool, const double* noise_dev);
