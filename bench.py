@@ -68,6 +68,25 @@ def ncu_dram_traffic_per_launch():
         return None
 
 
+def tree_roofline(pd, tree_ms, peaks):
+    """HBM roofline of the two tree kernels from the run's own counters (SURVEY 8(d) byte model with
+    f64 priors: child record visits 4 + value_sum 8 + prior 8 = 20 B, node header 16 B, path entry 4 B,
+    state 17 B; expansion writes 26 B per child and reads 4*65 + 4 B of evaluator output; backup is a
+    12 B read + 12 B write per path node)."""
+    sims, depth, scanned = pd["simulations"], pd["depth_sum"], pd["children_scanned"]
+    created, evals = pd["children_created"], pd["leaf_evals"]
+    select_bytes = 16 * depth + 20 * scanned + 17 * sims + 4 * (depth + sims)
+    expand_bytes = evals * (16 + 4 * 65 + 4) + 26 * created + 24 * (depth + sims)
+    peak = float(peaks.get("hbm_gbs", 6650.0)) if peaks else 6650.0
+    out = {"bound": "hbm", "peak": peak, "unit": "GB/s",
+           "note": "pointer-chasing kernels: dependent-load latency bound, far below the bandwidth roofline by construction"}
+    for name, nbytes in (("select", select_bytes), ("expand_backup", expand_bytes)):
+        ms = tree_ms.get(name, 0.0)
+        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
+        out[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved": gbs, "frac": gbs / peak if gbs else None}
+    return out
+
+
 def workload_config(args):
     game, grid, sims, cutoff, alpha = WORKLOADS[args.workload]
     return {"game": game, "grid": grid, "num_simulations": sims, "sample_move_cutoff": cutoff,
@@ -224,6 +243,7 @@ def run_b200(args):
     for pdn in engine.device_nets:
         pdn.profile(True)
     p0 = engine.counters()
+    engine.tree_timers = [] if args.pools == 1 else None
     pstart, pstop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     prof_steps = min(args.steps, 3)
     pstart.record()
@@ -238,6 +258,11 @@ def run_b200(args):
             prof[k] = (prof.get(k, (0.0, 0))[0] + ms, prof.get(k, (0.0, 0))[1] + cnt)
         pdn.profile(False)
     p1 = engine.counters()
+    tree_ms = {"select": 0.0, "expand_backup": 0.0}
+    for name, a, b in (engine.tree_timers or []):
+        tree_ms[name] += a.elapsed_time(b)
+    engine.tree_timers = None
+    pd = {k: p1[k] - p0[k] for k in p1}
     prof_leaf_evals = p1["leaf_evals"] - p0["leaf_evals"]
     engine.use_graph = was_graph
 
@@ -314,14 +339,14 @@ def run_b200(args):
         flop_per_leaf_conv = 2.0 * g * g * 9 * 128 * 128  # 18.87 MFLOP at g=8, 14.45 at g=7
         conv_ms, conv_launches = prof["trunk_conv"]
         peaks = {}
-        peak_src = "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst)"
+        peak_src = "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, 6.65 TB/s)"
         peak_tflops = 1590.0
         try:
             peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
             peak_tflops = float(peaks["bf16_tflops_sustained"])
             peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         except Exception:
-            pass
+            peaks = {}
         achieved = (prof_leaf_evals * 7 * flop_per_leaf_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
         line = {
             "metric": METRIC, "value": tot_sims / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -351,7 +376,8 @@ def run_b200(args):
                 "timed_in": f"{prof_steps} extra steps launched kernel by kernel right after the timed region "
                             "(CUDA events cannot be timed inside the replayed graph)",
             },
-            "kernel_ms": {k: v[0] for k, v in prof.items()},
+            "kernel_ms": {**{k: v[0] for k, v in prof.items()}, **tree_ms},
+            "tree_roofline": tree_roofline(pd, tree_ms, peaks),
             "tree_stats": {"mean_depth": d["depth_sum"] / max(1, d["simulations"]),
                            "children_scanned_per_sim": d["children_scanned"] / max(1, d["simulations"]),
                            "terminal_fraction": d["terminal_sims"] / max(1, d["simulations"]),

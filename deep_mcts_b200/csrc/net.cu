@@ -58,6 +58,7 @@ struct dm_net {
 namespace {
 
 int net_alloc_bytes(dm_net* net, void** out, size_t bytes, bool zero) {
+    if (*out) return DM_OK;  // already allocated by an earlier dm_net_finalize: sizes depend only on the config
     void* p = nullptr;
     DM_CUDA(cudaMalloc(&p, bytes ? bytes : 16));
     net->allocations.push_back(p);
@@ -68,7 +69,7 @@ int net_alloc_bytes(dm_net* net, void** out, size_t bytes, bool zero) {
 
 template <typename T>
 int net_upload(dm_net* net, T** out, const std::vector<T>& host) {
-    void* p = nullptr;
+    void* p = (void*)*out;
     int rc = net_alloc_bytes(net, &p, host.size() * sizeof(T), false);
     if (rc != DM_OK) return rc;
     DM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
@@ -315,13 +316,16 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
         return DM_ERR_INVALID;
     }
     DM_CUDA(cudaDeviceSynchronize());
-    free_device(net);
+    // Buffers are allocated on the first call and only refilled afterwards, so device pointers stay
+    // stable across weight transfers (captured CUDA graphs of the search round remain valid).
     net->NA2 = hw.NA2;
     DM_TRY(net_upload(net, &net->conv1_w, hw.conv1_w));
     DM_TRY(net_upload(net, &net->conv1_b, hw.conv1_b));
     const int L = 2 * R + 1;
-    net->trunk_w.assign(L, nullptr);
-    net->trunk_b.assign(L, nullptr);
+    if ((int)net->trunk_w.size() != L) {
+        net->trunk_w.assign(L, nullptr);
+        net->trunk_b.assign(L, nullptr);
+    }
     for (int l = 0; l < L; ++l) {
         DM_TRY(net_upload(net, &net->trunk_w[l], hw.trunk_w[l]));
         DM_TRY(net_upload(net, &net->trunk_b[l], hw.trunk_b[l]));
@@ -354,7 +358,7 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
     DM_TRY(net_alloc_bytes(net, (void**)&net->r_active, 16, true));
     net->bf16_ready = false;
     if (C == netk::kC && R >= 1) {
-        net->trunk_w16.assign(L, nullptr);
+        if ((int)net->trunk_w16.size() != L) net->trunk_w16.assign(L, nullptr);
         for (int l = 0; l < L; ++l) {
             std::vector<__nv_bfloat16> packed;
             pack_trunk_bf16(hw.trunk_w[l], C, packed);

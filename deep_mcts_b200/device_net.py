@@ -141,15 +141,28 @@ class DeviceNet:
         return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(("encode", "trunk_conv", "heads"))}
 
     # --------------------------------------------------------------------------- search
-    def search_round(self, pool, selfplay: bool = False) -> None:
-        """One select -> evaluate -> expand/backup round for every tree of the pool (no host sync)."""
+    def search_round(self, pool, selfplay: bool = False, timers: Optional[list] = None) -> None:
+        """One select -> evaluate -> expand/backup round for every tree of the pool (no host sync).
+        ``timers`` (a list) receives CUDA-event pairs around the two tree kernels:
+        ("select", start, stop), ("expand_backup", start, stop)."""
+        if timers is not None:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            ev[0].record()
         if selfplay:
             pool.selfplay_select()
         else:
             pool.select()
+        if timers is not None:
+            ev[1].record()
         value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity,
                                             pool.leaf_count)
+        if timers is not None:
+            ev[2].record()
         pool.expand_backup(probs, value)
+        if timers is not None:
+            ev[3].record()
+            timers.append(("select", ev[0], ev[1]))
+            timers.append(("expand_backup", ev[2], ev[3]))
 
     def run_search(self, pool, sims: int) -> None:
         """All armed simulations of one MCTS.step.  Exact mode: at most sims + 1 rounds (root

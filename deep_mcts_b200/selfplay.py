@@ -53,6 +53,7 @@ class BatchedSelfPlay:
         else:
             self._build_device_nets(per_pool)
         self.pool = self.pools[0]
+        self.tree_timers = None     # set to a list to collect CUDA-event pairs around the tree kernels
         self.use_graph = False      # set True to replay one captured round instead of re-launching it
         self._graph = None
         self._graph_launches = 0
@@ -88,7 +89,7 @@ class BatchedSelfPlay:
                 self.graph_replays += int(rounds)
                 return
             for _ in range(int(rounds)):
-                dn.search_round(pool, selfplay=True)
+                dn.search_round(pool, selfplay=True, timers=self.tree_timers)
             return
         current = torch.cuda.current_stream()
         for st in self.streams:

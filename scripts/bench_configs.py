@@ -144,9 +144,66 @@ def train(rank, world):
                           "train_steps_per_block": cfg.train_steps_per_block}))
 
 
+def engines(rank, world):
+    """Game-engine kernels alone (dm_game_*): states/s, plies/s and achieved GB/s against the HBM peak.
+    Bytes per state: 17 in (two bitboards + player) + the outputs of each call."""
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200.hex.game import HexManager
+    from deep_mcts_b200.othello.game import OthelloManager
+    n = 1 << 20
+    peak = 6538.9
+    try:
+        peak = float(json.load(open(ROOT / "MEASURED_PEAKS.json"))["hbm_gbs"])
+    except Exception:
+        pass
+    for manager, plies in ((OthelloManager(8), 20), (HexManager(7), 15)):
+        p, f, s = midgame_roots(manager, 4096, plies, seed=1)
+        idx = np.arange(n) % 4096
+        dev = manager.device
+        f_d = torch.from_numpy(f[idx].view(np.int64).copy()).to(dev)
+        s_d = torch.from_numpy(s[idx].view(np.int64).copy()).to(dev)
+        p_d = torch.from_numpy(p[idx].copy()).to(dev)
+        lst = torch.empty((n, 65), dtype=torch.uint8, device=dev)
+        order = torch.empty((n, 65), dtype=torch.uint8, device=dev)
+        cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        fin = torch.empty(n, dtype=torch.uint8, device=dev)
+        out = torch.empty(n, dtype=torch.float32, device=dev)
+        plies_d = torch.empty(n, dtype=torch.int32, device=dev)
+        act = torch.zeros(n, dtype=torch.int32, device=dev)
+        of, os_, op, ok = torch.empty_like(f_d), torch.empty_like(s_d), torch.empty_like(p_d), torch.empty_like(fin)
+        st = torch.cuda.current_stream().cuda_stream
+        gid, g = manager.game_id, manager.board
+        calls = {
+            "legal (list + set order)": (lambda: _lib.call("dm_game_legal", gid, g, n, f_d.data_ptr(), s_d.data_ptr(), p_d.data_ptr(), lst.data_ptr(), order.data_ptr(), cnt.data_ptr(), st), 17 + 130 + 4),
+            "status": (lambda: _lib.call("dm_game_status", gid, g, n, f_d.data_ptr(), s_d.data_ptr(), p_d.data_ptr(), fin.data_ptr(), out.data_ptr(), st), 17 + 5),
+            "child": (lambda: _lib.call("dm_game_child", gid, g, n, f_d.data_ptr(), s_d.data_ptr(), p_d.data_ptr(), act.data_ptr(), of.data_ptr(), os_.data_ptr(), op.data_ptr(), ok.data_ptr(), st), 17 + 4 + 18),
+            "random rollout": (lambda: _lib.call("dm_game_rollout", gid, g, n, f_d.data_ptr(), s_d.data_ptr(), p_d.data_ptr(), _lib.DM_ROLLOUT_RANDOM, 7, out.data_ptr(), plies_d.data_ptr(), st), 17 + 8),
+        }
+        _lib.call("dm_game_legal", gid, g, n, f_d.data_ptr(), s_d.data_ptr(), p_d.data_ptr(), lst.data_ptr(), 0, cnt.data_ptr(), st)
+        act.copy_(lst[:, 0].to(torch.int32))
+        for name, (fn, nbytes) in calls.items():
+            for _ in range(3):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 5
+            line = {"config": f"{type(manager).__name__}({g}) dm_game: {name}", "states": n, "ms": ms,
+                    "states_per_sec": n / (ms * 1e-3), "algorithmic_bytes_per_state": nbytes,
+                    "achieved_GBps": n * nbytes / (ms * 1e-3) / 1e9, "hbm_peak_GBps": peak,
+                    "frac": n * nbytes / (ms * 1e-3) / 1e9 / peak}
+            if name == "random rollout":
+                line["plies_per_sec"] = float(plies_d.sum().item()) / (ms * 1e-3)
+            if rank == 0:
+                print(json.dumps(line))
+
+
 if __name__ == "__main__":
     rank, world = setup()
     which = sys.argv[1] if len(sys.argv) > 1 else "rollouts"
-    {"rollouts": rollouts, "train": train}[which](rank, world)
+    {"rollouts": rollouts, "train": train, "engines": engines}[which](rank, world)
     if world > 1:
         dist.destroy_process_group()

@@ -95,3 +95,40 @@ def test_selfplay_with_device_net_runs_and_labels_consistently():
     engine2.run_rounds(100)
     torch.cuda.synchronize()
     assert engine2.counters()["games"] > 10
+
+
+def test_weight_transfer_keeps_graph_valid_and_changes_outputs():
+    """Re-packing weights (the reference's weight transfer, train.py:169-171) must update the kernels'
+    weights in place: outputs follow the new weights and a captured CUDA graph of the round stays valid."""
+    from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
+    from deep_mcts_b200.selfplay import BatchedSelfPlay
+    from oracle import net as onet
+    from oracle.games import make_game
+    from oracle.synth import random_positions, synthetic_state_dict
+    game = make_game("othello", 6)
+    states = random_positions(game, 64, seed=3)
+    p = [s[0] for s in states]; f = [s[1] for s in states]; s2 = [s[2] for s in states]
+    net = ConvolutionalOthelloNet(6)
+    net.precision = "fp32"
+    sd_a = synthetic_state_dict(game, 128, 3, 128, seed=1, conv_gain=1.0, fc_scale=1.0)
+    sd_b = synthetic_state_dict(game, 128, 3, 128, seed=2, conv_gain=1.0, fc_scale=1.0)
+    net.load_state_dict(sd_a)
+    engine = BatchedSelfPlay(net, 128, 8, sample_move_cutoff=2, dirichlet_alpha=1.0, seed=1)
+    engine.use_graph = True
+    engine.run_rounds(30)
+    dn = engine.device_nets[0]
+    va, pa = dn.evaluate(p, f, s2)
+    want_a = onet.evaluate_batch(game, sd_a, states)
+    np.testing.assert_allclose(pa, want_a[1], atol=1e-5, rtol=0)
+    net.load_state_dict(sd_b)
+    engine.sync_weights()
+    vb, pb = dn.evaluate(p, f, s2)
+    want_b = onet.evaluate_batch(game, sd_b, states)
+    np.testing.assert_allclose(pb, want_b[1], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(vb, want_b[0], atol=1e-5, rtol=0)
+    assert np.abs(pa - pb).max() > 1e-3
+    before = engine.counters()["simulations"]
+    engine.run_rounds(30)          # replays the graph captured before the transfer
+    torch.cuda.synchronize()
+    c = engine.counters()
+    assert c["simulations"] > before and c["capacity_errors"] == 0
