@@ -305,3 +305,42 @@ def test_full_size_pool_consistency_and_oracle_subset():
         batch.advance(actions)
     c = batch.pool.counters()
     assert c["simulations"] - c_before["simulations"] == T * sims * 4 and c["capacity_errors"] == 0
+
+
+def test_capacity_error_is_reported_not_silent():
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200 import mcts as dm
+    manager = manager_for("othello", 8)
+    m = dm.MCTS(manager, 200, None, dm.uniform_state_evaluator(manager), max_nodes_per_tree=64)
+    with pytest.raises(_lib.DeepMctsError) as err:
+        m.step()
+    assert err.value.code == _lib.DM_ERR_CAPACITY
+
+
+def test_time_budget_mode_and_illegal_action():
+    from deep_mcts_b200 import mcts as dm
+    manager = manager_for("hex", 5)
+    m = dm.MCTS(manager, float("inf"), dm.random_rollout_policy(manager), None, time_per_move=0.2)
+    dist, (with_exp, without_exp) = m.step()
+    assert with_exp + without_exp >= 64 and abs(sum(dist) - 1) < 1e-9
+    with pytest.raises(AssertionError):
+        m.advance(0) if False else manager.generate_child_state(
+            manager.generate_child_state(manager.initial_game_state(), 0), 0)
+    # advancing the pool by an illegal action is counted, not applied
+    before = m.pool.counters()["invalid_actions"]
+    m.pool.advance([manager.num_actions + 5])
+    assert m.pool.counters()["invalid_actions"] == before + 1
+
+
+def test_odd_tree_counts_and_reset_subset():
+    from deep_mcts_b200 import mcts as dm
+    manager = manager_for("tictactoe", 3)
+    b = dm.BatchedMCTS(manager, 7, 16, None, dm.hashed_state_evaluator(manager, 1))
+    v1, _ = b.step()
+    b.advance(np.argmax(v1, axis=1).astype(np.int32))
+    b.reset([0, 3])
+    p, f, s, fin, _ = b.pool.states()
+    assert f[0] == 0 and s[0] == 0 and f[3] == 0 and (f[1] | s[1]) != 0
+    v2, st = b.step()
+    assert (st.sum(axis=1) == 16).all()
+    assert (v2[0] == v1[0]).all()          # a reset tree repeats its first search exactly
