@@ -25,7 +25,7 @@ LIB_PATH = Path(__file__).resolve().parent / "libdeepmcts_b200.so"
 class PoolConfig(ctypes.Structure):
     _fields_ = [
         ("game", c_int32), ("grid", c_int32), ("n_trees", c_int32), ("max_nodes_per_tree", c_int32),
-        ("device", c_int32), ("reserved0", c_int32), ("c_puct", c_double), ("seed", c_uint64),
+        ("device", c_int32), ("compaction", c_int32), ("c_puct", c_double), ("seed", c_uint64),
     ]
 
 

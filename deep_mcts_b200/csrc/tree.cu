@@ -28,7 +28,8 @@ constexpr u8 kLeafRoot = 1;  // leaf is a root expansion: only root.visits += 1 
 
 enum Counter {
     kCntSims = 0, kCntLeafEvals = 1, kCntTerminal = 2, kCntNodesHigh = 3, kCntGames = 4, kCntDepth = 5,
-    kCntScanned = 6, kCntCreated = 7, kCntCapacity = 8, kCntMoves = 9, kCntRolloutPlies = 10, kCntInvalid = 11
+    kCntScanned = 6, kCntCreated = 7, kCntCapacity = 8, kCntMoves = 9, kCntRolloutPlies = 10, kCntInvalid = 11,
+    kCntCompactions = 12
 };
 
 struct PoolView {
@@ -77,6 +78,10 @@ struct PoolView {
     int* vl_slot;   // [n_trees][DM_MAX_LEAVES] leaf-batch slot of each pending path
     int* vl_count;  // [n_trees]
     int* armed;     // number of trees that still have simulations left after the last select
+    // arena compaction scratch (null = compaction disabled): live-node bitmap and per-word prefix counts
+    u32* cmark;     // [n_trees][cap_words]
+    u32* cprefix;   // [n_trees][cap_words]
+    u32 cap_words;
     unsigned long long* counters;
     // self-play recording
     int selfplay;
@@ -344,6 +349,109 @@ __device__ __forceinline__ double mix_rollout(const PoolView& P, const GState& s
     return __ddiv_rn(__dadd_rn(r, eval_value), 2.0);
 }
 
+// ---- arena compaction ---------------------------------------------------------------------
+// Re-rooting with subtree reuse (mcts.py:105-108) leaves the rest of the old tree unreachable.
+// When a tree's arena is more than half full at a re-root, the live subtree is slid to the front
+// in place: (1) mark live nodes in one forward pass (children are always allocated after their
+// parent, so marks flow forward), (2) prefix-count the marks per 32-node word, (3) move every
+// live node to its rank.  Order is preserved, so contiguous child blocks stay contiguous, ranks
+// never exceed the old index (in-place safe) and the child order -- hence tie-breaking -- is
+// unchanged.  Whole warp.
+__device__ __forceinline__ u32 live_rank(const u32* mark, const u32* prefix, u32 x) {
+    return prefix[x >> 5] + __popc(mark[x >> 5] & ((1u << (x & 31)) - 1u));
+}
+
+__device__ __forceinline__ void compact_tree(const PoolView& P, int t, int lane) {
+    if (!P.cmark) return;
+    const u32 used = P.node_count[t];
+    if (used <= P.cap / 2) return;
+    const size_t base = (size_t)t * P.cap;
+    u32* mark = P.cmark + (size_t)t * P.cap_words;
+    u32* prefix = P.cprefix + (size_t)t * P.cap_words;
+    const u32 nw = (used + 31) >> 5;
+    const u32 root = P.root[t];
+    for (u32 w = lane; w < nw; w += 32) mark[w] = 0;
+    __syncwarp();
+    if (lane == 0) mark[root >> 5] = 1u << (root & 31);
+    __syncwarp();
+    // (1) forward marking
+    for (u32 w = root >> 5; w < nw; ++w) {
+        u32 processed = 0;
+        while (true) {
+            u32 word = mark[w];
+            u32 todo = word & ~processed;
+            if (!todo) break;
+            if ((todo >> lane) & 1) {
+                size_t idx = base + ((size_t)w << 5) + lane;
+                u32 n = P.n_children[idx];
+                u32 fc = P.first_child[idx];
+                if (n && fc != 0xffffffffu) {
+                    u32 lo = fc, hi = fc + n;  // [lo, hi)
+                    for (u32 ww = lo >> 5; ww <= (hi - 1) >> 5; ++ww) {
+                        u32 a = max(lo, ww << 5) - (ww << 5), b = min(hi, (ww + 1) << 5) - (ww << 5);  // bit range [a, b)
+                        u32 bits = (b == 32 ? 0xffffffffu : ((1u << b) - 1u)) & ~((1u << a) - 1u);
+                        atomicOr(&mark[ww], bits);
+                    }
+                }
+            }
+            processed |= todo;
+            __syncwarp();
+        }
+    }
+    // (2) exclusive prefix of popcounts per word
+    u32 running = 0;
+    for (u32 w0 = 0; w0 < nw; w0 += 32) {
+        u32 w = w0 + lane;
+        u32 c = (w < nw) ? __popc(mark[w]) : 0;
+        u32 incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            u32 v = __shfl_up_sync(DM_FULL_MASK, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (w < nw) prefix[w] = running + incl - c;
+        running += __shfl_sync(DM_FULL_MASK, incl, 31);
+    }
+    __syncwarp();
+    // (3) slide live nodes to their ranks, lowest index first
+    for (u32 w = root >> 5; w < nw; ++w) {
+        u32 word = mark[w];
+        bool live = (word >> lane) & 1;
+        size_t src = base + ((size_t)w << 5) + lane;
+        u32 v = 0, fc = 0;
+        double vs = 0.0, pr = 0.0;
+        u8 nc = 0, ac = 0;
+        u32 dst = 0;
+        if (live) {
+            v = P.visits[src];
+            vs = P.value_sum[src];
+            pr = P.prior[src];
+            fc = P.first_child[src];
+            nc = P.n_children[src];
+            ac = P.action[src];
+            dst = prefix[w] + __popc(word & ((1u << lane) - 1u));
+            if (nc) fc = live_rank(mark, prefix, fc);
+        }
+        __syncwarp();
+        if (live) {
+            size_t d = base + dst;
+            P.visits[d] = v;
+            P.value_sum[d] = vs;
+            P.prior[d] = pr;
+            P.first_child[d] = fc;
+            P.n_children[d] = nc;
+            P.action[d] = ac;
+        }
+        __syncwarp();
+    }
+    if (lane == 0) {
+        P.root[t] = 0;
+        P.node_count[t] = running;
+        count(P, kCntCompactions, 1);
+    }
+    __syncwarp();
+}
+
 // --------------------------------------------------------------------- kernels: admin
 __global__ void k_reset(PoolView P, const int* ids, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -412,6 +520,8 @@ __global__ void k_observe(PoolView P, const int* ids, int n, const u64* first, c
         }
         P.sims_left[t] = 0;
     }
+    __syncwarp();
+    compact_tree(P, t, lane);
 }
 
 __global__ void k_begin_step(PoolView P) {
@@ -643,6 +753,7 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
     }
     if (lane == 0) count(P, kCntMoves, 1);
     __syncwarp();
+    compact_tree(P, t, lane);
     if (lane == 0) arm_step(P, t);
     __syncwarp();
 }
@@ -1018,26 +1129,32 @@ __global__ void k_advance(PoolView P, const int* actions) {
         if (P.action[base + first + j] == a) child = j;
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) child = max(child, __shfl_xor_sync(DM_FULL_MASK, child, off));
-    if (lane != 0) return;
     GState s = root_state(P, t);
+    bool moved = true;
     if (child < 0) {
         // root not expanded (or action illegal): follow the reference's Node() fallback
         // only when the action is legal; otherwise flag it
         if (!game_action_legal(P.cfg, s, a)) {
-            count(P, kCntInvalid, 1);
-            return;
+            if (lane == 0) count(P, kCntInvalid, 1);
+            moved = false;
+        } else if (lane == 0) {
+            fresh_root(P, t, game_child(P.cfg, s, a));
         }
-        fresh_root(P, t, game_child(P.cfg, s, a));
-    } else {
+    } else if (lane == 0) {
         GState ns = game_child(P.cfg, s, a);
         P.root[t] = first + (u32)child;
         P.root_first[t] = ns.first;
         P.root_second[t] = ns.second;
         P.root_player[t] = (u8)ns.player;
     }
-    P.ply[t] += 1;
-    P.sims_left[t] = 0;
-    P.flags[t] &= ~(kFlagNeedNoise | kFlagStepActive);
+    if (!moved) return;
+    if (lane == 0) {
+        P.ply[t] += 1;
+        P.sims_left[t] = 0;
+        P.flags[t] &= ~(kFlagNeedNoise | kFlagStepActive);
+    }
+    __syncwarp();
+    compact_tree(P, t, lane);
 }
 
 __global__ void k_states(PoolView P, u64* first, u64* second, u8* player, u8* is_final, float* outcome) {
@@ -1131,6 +1248,11 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
         (rc = pool_alloc(p, &v.vl_count, T)) || (rc = pool_alloc(p, &v.armed, 1)) ||
         (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)))
         return fail(rc);
+    if (cfg->compaction) {
+        v.cap_words = (v.cap + 31) / 32;
+        if ((rc = pool_alloc(p, &v.cmark, T * v.cap_words, false)) || (rc = pool_alloc(p, &v.cprefix, T * v.cap_words, false)))
+            return fail(rc);
+    }
     k_reset<<<(cfg->n_trees + 127) / 128, 128>>>(v, nullptr, cfg->n_trees);
     ++g_dm_launches;
     cudaError_t e = cudaDeviceSynchronize();

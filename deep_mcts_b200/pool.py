@@ -40,13 +40,16 @@ def default_node_capacity(manager: BoardManager, num_simulations: int) -> int:
 
 class TreePool:
     def __init__(self, manager: BoardManager, n_trees: int, max_nodes_per_tree: int = 1 << 16, seed: int = 0,
-                 c_puct: float = 1.25) -> None:
+                 c_puct: float = 1.25, compaction: bool = True) -> None:
+        """``compaction``: slide a tree's live subtree to the front of its arena at a re-root once the
+        arena is more than half full, so long games / long searches never outgrow ``max_nodes_per_tree``
+        as long as one move's search fits in half of it."""
         self.manager = manager
         self.n_trees = int(n_trees)
         self.device = manager.device
         self.num_actions = manager.num_actions
         cfg = _lib.PoolConfig(manager.game_id, manager.board, self.n_trees, int(max_nodes_per_tree),
-                              self.device.index or 0, 0, float(c_puct), int(seed))
+                              self.device.index or 0, 1 if compaction else 0, float(c_puct), int(seed))
         handle = _lib.c_void_p()
         _lib.call("dm_pool_create", cfg, handle)
         self._h = handle
@@ -234,7 +237,7 @@ class TreePool:
 
     COUNTER_NAMES = ("simulations", "leaf_evals", "terminal_sims", "nodes_high_water", "games", "depth_sum",
                      "children_scanned", "children_created", "capacity_errors", "moves", "rollout_plies",
-                     "invalid_actions")
+                     "invalid_actions", "compactions")
 
     def counters(self) -> dict:
         out = (_lib.c_uint64 * 16)()

@@ -73,7 +73,8 @@ typedef struct {
     int32_t n_trees;             /* independent trees (games) in the pool */
     int32_t max_nodes_per_tree;  /* node arena per tree */
     int32_t device;              /* CUDA device ordinal */
-    int32_t reserved0;
+    int32_t compaction;          /* 1 = compact a tree's arena in place at a re-root when it is more than half
+                                    full (subtree reuse, mcts.py:105-108, without unbounded growth) */
     double c_puct;               /* 1.25 in the reference (mcts.py:42) */
     uint64_t seed;               /* Philox key for device-side sampling */
 } dm_pool_config;
@@ -189,7 +190,7 @@ int dm_pool_states(dm_pool* pool, uint64_t* first_dev, uint64_t* second_dev, uin
 /* counters since creation (synchronises): [0] simulations, [1] leaf evaluations requested,
  * [2] terminal simulations, [3] nodes allocated high-water, [4] games finished (self-play),
  * [5] sum of selection depths, [6] children scanned, [7] children created, [8] capacity errors,
- * [9] moves played (self-play), [10] rollout plies */
+ * [9] moves played (self-play), [10] rollout plies, [11] invalid actions, [12] arena compactions */
 int dm_pool_counters(dm_pool* pool, uint64_t out[16]);
 
 /* --------------------------------------------------- continuous batched self-play

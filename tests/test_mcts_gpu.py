@@ -344,3 +344,32 @@ def test_odd_tree_counts_and_reset_subset():
     v2, st = b.step()
     assert (st.sum(axis=1) == 16).all()
     assert (v2[0] == v1[0]).all()          # a reset tree repeats its first search exactly
+
+
+@pytest.mark.parametrize("name,g,kind", [("othello", 8, "hashed"), ("hex", 7, "uniform")])
+def test_arena_compaction_preserves_exactness(name, g, kind):
+    """A whole game in an arena far smaller than the game's total node count: the in-place compaction
+    at re-roots must keep visit counts, child order and root visits bit-identical to the oracle."""
+    from deep_mcts_b200 import mcts as dm
+    game = make_game(name, g)
+    manager = manager_for(name, g)
+    sims = 40
+    ev = dm.hashed_state_evaluator(manager, 0) if kind == "hashed" else dm.uniform_state_evaluator(manager)
+    # room for the reused subtree plus one move of growth, still ~10x less than the whole game creates
+    small = dm.MCTS(manager, sims, None, ev, max_nodes_per_tree=(sims + 2) * game.num_actions * 4)
+    ref = OracleMCTS(game, sims, None, oev.hashed if kind == "hashed" else oev.uniform)
+    moves = 0
+    while not game.is_final(ref.state) and moves < 40:
+        dist, stats = small.step()
+        ref_dist, ref_stats = ref.step()
+        assert dist == ref_dist and tuple(stats) == tuple(ref_stats), moves
+        order, count, root_visits = small.pool.root_children()
+        assert [int(a) for a in order[0, :count[0]]] == ref.root_children_actions()
+        assert int(root_visits[0]) == ref.visits[ref.root]
+        a = int(np.argmax(ref_dist))
+        small.advance(a)
+        ref.advance(a)
+        moves += 1
+    c = small.pool.counters()
+    assert c["compactions"] >= 2 and c["capacity_errors"] == 0, c
+    assert c["children_created"] > small.pool._search.num_simulations  # far more nodes created than the arena holds
