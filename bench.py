@@ -394,7 +394,9 @@ def run_b200(args):
                 "leaf_evals_per_sec": ce / cw,
                 "sample": f"{procs} processes x 1 torch thread x {args.cpu_seconds:.0f} s of full self-play games "
                           "with the same net/config (oracle port of the reference loop; the Python reference "
-                          "itself is not present on the GPU box)"}
+                          "itself is not present on the GPU box)",
+                "calibration": "in the build container the port runs 1.19x faster per process than the unmodified "
+                               "reference (331 vs 278 sims/s), see DESIGN.md section 6"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
