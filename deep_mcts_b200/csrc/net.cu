@@ -26,6 +26,7 @@ struct dm_net {
     size_t rows_total = 0;
     // fp32 weights
     float *conv1_w = nullptr, *conv1_b = nullptr;
+    float *conv1_tab = nullptr, *conv1_base = nullptr;  // k_encode_conv1_table operands
     std::vector<float*> trunk_w, trunk_b;
     float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_t = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
     float vconv_b = 0.f, vfc2_b = 0.f;
@@ -203,11 +204,10 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         return DM_ERR_INVALID;
     }
     int pe = prof_begin(net, 0, st);
-    {
-        size_t smem2 = (size_t)(27 * C + C + 16 * C) * sizeof(float) + (size_t)netk::kEncode2Boards * gp * gp + 16;
-        netk::k_encode_conv1_sparse<<<(n + netk::kEncode2Boards - 1) / netk::kEncode2Boards, 256, smem2, st>>>(
-            g, n, count_dev, first, second, player, net->conv1_w, net->conv1_b, C, net->a0, net->rows_total);
-    }
+    netk::k_encode_conv1_table<<<(n + netk::kEncode3Boards - 1) / netk::kEncode3Boards, 256,
+                                 netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, first, second, player,
+                                                                         net->conv1_tab, net->conv1_base, C, net->a0,
+                                                                         net->rows_total);
     prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
     const bool v1 = net->conv_v1;
@@ -363,6 +363,39 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
             std::vector<__nv_bfloat16> packed;
             pack_trunk_bf16(hw.trunk_w[l], C, packed);
             DM_TRY(net_upload(net, &net->trunk_w16[l], packed));
+        }
+        {
+            // first-conv tables: tab[dy][pattern of 3 cells][C] and base[player][border class][C]
+            std::vector<float> tab((size_t)3 * 27 * C, 0.f), basev((size_t)2 * 16 * C, 0.f);
+            for (int dy = 0; dy < 3; ++dy)
+                for (int pat = 0; pat < 27; ++pat) {
+                    const int code[3] = {pat % 3, (pat / 3) % 3, pat / 9};
+                    for (int dx = 0; dx < 3; ++dx) {
+                        if (!code[dx]) continue;
+                        const int tap = dy * 3 + dx, plane = code[dx] - 1;
+                        for (int c = 0; c < C; ++c)
+                            tab[((size_t)dy * 27 + pat) * C + c] += hw.conv1_w[((size_t)tap * 3 + plane) * C + c];
+                    }
+                }
+            for (int pl = 0; pl < 2; ++pl)
+                for (int cls = 0; cls < 16; ++cls) {
+                    const int ym = cls & 3, xm = cls >> 2;
+                    for (int c = 0; c < C; ++c) {
+                        float acc = hw.conv1_b[c];
+                        if (pl)
+                            for (int tap = 0; tap < 9; ++tap) {
+                                const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                                const bool yin = dy == 0 || (dy < 0 ? (ym & 1) : (ym & 2));
+                                const bool xin = dx == 0 || (dx < 0 ? (xm & 1) : (xm & 2));
+                                if (yin && xin) acc += hw.conv1_w[((size_t)tap * 3 + 2) * C + c];
+                            }
+                        basev[((size_t)pl * 16 + cls) * C + c] = acc;
+                    }
+                }
+            DM_TRY(net_upload(net, &net->conv1_tab, tab));
+            DM_TRY(net_upload(net, &net->conv1_base, basev));
+            DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)netk::encode3_smem_bytes(C, g)));
         }
         // policy FC weights as the tcgen05 B operand: [(pos*16 + kc)][a][8 channels]
         net->fc_na = netk::fc_padded_actions(A);

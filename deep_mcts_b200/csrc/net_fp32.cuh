@@ -237,6 +237,99 @@ __global__ void __launch_bounds__(256) k_encode_conv1_sparse(GameCfg cfg, int n,
     }
 }
 
+// Table-driven variant (the one the bf16 path runs): because every input cell is own / opponent /
+// empty, the contribution of one board row to an output is a function of just 3 cells = 27
+// patterns.  The host folds the weights into  tab[dy][pattern][C]  (pattern = c(x-1) + 3 c(x) +
+// 9 c(x+1)) and  base[player][border class][C]  (bias + the in-board taps of the constant player
+// plane), so an output chunk is 4 branch-free table reads: base + tab[-1] + tab[0] + tab[+1].
+constexpr int kEncode3Boards = 8;
+inline size_t encode3_smem_bytes(int C, int g) {
+    // table rows are padded by 4 floats in shared memory: lanes of a warp read DIFFERENT rows (their
+    // 3-cell patterns differ) at the same column, and an unpadded 512-byte row pitch would put all of
+    // them on the same banks
+    return (size_t)(3 * 27 + 2 * 16) * (C + 4) * sizeof(float) + (size_t)kEncode3Boards * (g + 2) * (g + 2) + 64;
+}
+__global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, const int* count_dev,
+                                                            const u64* first, const u64* second, const u8* player,
+                                                            const float* __restrict__ tab,   // [3][27][C]
+                                                            const float* __restrict__ basev,  // [2][16][C]
+                                                            int C, __nv_bfloat16* out_bf16, size_t rows_total) {
+    extern __shared__ __align__(16) float smem[];
+    const int g = cfg.g, gp = g + 2, P0 = g * g;
+    const int CP = C + 4;                // padded row pitch
+    float* s_tab = smem;                 // [3*27][CP]
+    float* s_base = s_tab + 81 * CP;     // [2*16][CP]
+    u8* s_code = reinterpret_cast<u8*>(s_base + 32 * CP);
+    __shared__ int s_player[kEncode3Boards];
+    const int live = live_count(count_dev, n);
+    const int b0 = blockIdx.x * kEncode3Boards;
+    if (b0 >= live) return;
+    {
+        const int c4 = C / 4;
+        const float4* src = reinterpret_cast<const float4*>(tab);
+        for (int i = threadIdx.x; i < 81 * c4; i += blockDim.x)
+            *reinterpret_cast<float4*>(s_tab + (i / c4) * CP + (i % c4) * 4) = __ldg(src + i);
+        const float4* src2 = reinterpret_cast<const float4*>(basev);
+        for (int i = threadIdx.x; i < 32 * c4; i += blockDim.x)
+            *reinterpret_cast<float4*>(s_base + (i / c4) * CP + (i % c4) * 4) = __ldg(src2 + i);
+    }
+    for (int i = threadIdx.x; i < kEncode3Boards * gp * gp; i += blockDim.x) {
+        int bb = i / (gp * gp), r = i % (gp * gp);
+        int b = b0 + bb;
+        u8 code = 0;
+        int y = r / gp - 1, x = r % gp - 1;
+        if (b < live && y >= 0 && y < g && x >= 0 && x < g) {
+            int pl = player[b];
+            bool transpose = (cfg.game == DM_HEX || cfg.game == DM_HEX_SWAP) && pl == 0;
+            int bit = transpose ? (x * g + y) : (y * g + x);
+            u64 f = first[b], s2 = second[b];
+            u64 own = pl ? f : s2, opp = pl ? s2 : f;
+            code = ((own >> bit) & 1) ? 1 : (((opp >> bit) & 1) ? 2 : 0);
+        }
+        s_code[i] = code;
+    }
+    if (threadIdx.x < kEncode3Boards) s_player[threadIdx.x] = (b0 + threadIdx.x < live) ? player[b0 + threadIdx.x] : 0;
+    __syncthreads();
+    const RowGeom geom = RowGeom::make(g);
+    const int chunks = C / 8;
+    const int pos = threadIdx.x & 63, q = threadIdx.x >> 6;
+    if (pos >= P0) return;
+    const int y = pos / g, x = pos % g;
+    const int cls = (y > 0) + 2 * (y < g - 1) + 4 * ((x > 0) + 2 * (x < g - 1));
+    for (int bb = 0; bb < kEncode3Boards; ++bb) {
+        const int b = b0 + bb;
+        if (b >= live) break;
+        const u8* code = s_code + bb * gp * gp + y * gp + x;   // top-left of the 3x3 window (padded coords)
+        const float* t0 = s_tab + (0 * 27 + code[0] + 3 * code[1] + 9 * code[2]) * CP;
+        const float* t1 = s_tab + (1 * 27 + code[gp] + 3 * code[gp + 1] + 9 * code[gp + 2]) * CP;
+        const float* t2 = s_tab + (2 * 27 + code[2 * gp] + 3 * code[2 * gp + 1] + 9 * code[2 * gp + 2]) * CP;
+        const float* bs = s_base + ((s_player[bb] ? 16 : 0) + cls) * CP;
+        const size_t row = (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
+        for (int kc = q; kc < chunks; kc += 4) {
+            float a[8];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float4 v0 = *reinterpret_cast<const float4*>(bs + kc * 8 + 4 * h);
+                const float4 v1 = *reinterpret_cast<const float4*>(t0 + kc * 8 + 4 * h);
+                const float4 v2 = *reinterpret_cast<const float4*>(t1 + kc * 8 + 4 * h);
+                const float4 v3 = *reinterpret_cast<const float4*>(t2 + kc * 8 + 4 * h);
+                a[4 * h + 0] = fmaxf((v0.x + v1.x) + (v2.x + v3.x), 0.f);
+                a[4 * h + 1] = fmaxf((v0.y + v1.y) + (v2.y + v3.y), 0.f);
+                a[4 * h + 2] = fmaxf((v0.z + v1.z) + (v2.z + v3.z), 0.f);
+                a[4 * h + 3] = fmaxf((v0.w + v1.w) + (v2.w + v3.w), 0.f);
+            }
+            __nv_bfloat162 q0 = __floats2bfloat162_rn(a[0], a[1]), q1 = __floats2bfloat162_rn(a[2], a[3]);
+            __nv_bfloat162 q2 = __floats2bfloat162_rn(a[4], a[5]), q3 = __floats2bfloat162_rn(a[6], a[7]);
+            uint4 v;
+            v.x = *reinterpret_cast<u32*>(&q0);
+            v.y = *reinterpret_cast<u32*>(&q1);
+            v.z = *reinterpret_cast<u32*>(&q2);
+            v.w = *reinterpret_cast<u32*>(&q3);
+            *reinterpret_cast<uint4*>(out_bf16 + ((size_t)kc * rows_total + row) * 8) = v;
+        }
+    }
+}
+
 // fp32 3x3 conv C -> C + bias (+ residual) + ReLU on NHWC activations, one block per board.
 // Thread item = (output channel, strip of up to 8 positions).
 __global__ void __launch_bounds__(256) k_conv3x3_f32(int g, int C, int n, const int* count_dev,
