@@ -19,7 +19,8 @@ DM_ROLLOUT_NONE, DM_ROLLOUT_RANDOM, DM_ROLLOUT_MIN_ACTION, DM_ROLLOUT_MAX_ACTION
 
 DM_ERR_INVALID, DM_ERR_CUDA, DM_ERR_CAPACITY, DM_ERR_STATE = -1, -2, -3, -4
 
-LIB_PATH = Path(__file__).resolve().parent / "libdeepmcts_b200.so"
+# DM_LIB_PATH selects another build of the same library (A/B experiments); there is still no fallback.
+LIB_PATH = Path(os.environ.get("DM_LIB_PATH") or (Path(__file__).resolve().parent / "libdeepmcts_b200.so"))
 
 
 class PoolConfig(ctypes.Structure):

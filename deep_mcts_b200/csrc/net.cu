@@ -37,6 +37,7 @@ struct dm_net {
     __nv_bfloat16* pfc_w16 = nullptr;  // [g*g*16][NA][8] (k_policy_fc_tc B operand)
     int fc_na = 0, fc_split = 1;
     bool conv_v1 = false;  // DM_CONV_V1=1 selects the non-persistent trunk kernel (A/B testing)
+    bool pair_layout = false;  // 8x8 boards: pad-free interleaved layout (DM_NO_PAIR=1 disables, A/B testing)
     int sm_count = 148;
     float* fc_partial = nullptr;       // [split][max_batch rounded to 128][NA]
     // activations
@@ -207,16 +208,17 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     netk::k_encode_conv1_table<<<(n + netk::kEncode3Boards - 1) / netk::kEncode3Boards, 256,
                                  netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, first, second, player,
                                                                          net->conv1_tab, net->conv1_base, C, net->a0,
-                                                                         net->rows_total);
+                                                                         net->rows_total, net->pair_layout ? 1 : 0);
     prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
-    const bool v1 = net->conv_v1;
-    const size_t conv_smem = v1 ? netk::conv_smem_bytes(net->geom) : netk::conv2_smem_bytes(net->geom);
-    const int conv_items = (int)(((size_t)n * net->geom.P + netk::kItemRows - 1) / netk::kItemRows);
+    const bool v1 = net->conv_v1, pair = net->pair_layout;
+    const size_t conv_smem = v1 ? netk::conv_smem_bytes(net->geom)
+                                : (pair ? netk::conv2_smem_bytes_pair() : netk::conv2_smem_bytes(net->geom));
+    const int conv_items = pair ? (n + 3) / 4 : (int)(((size_t)n * net->geom.P + netk::kItemRows - 1) / netk::kItemRows);
     const int conv_blocks = v1 ? (int)(((size_t)n * net->geom.P + netk::kRowsPerCta - 1) / netk::kRowsPerCta)
                                : (conv_items < net->sm_count ? conv_items : net->sm_count);
     const int conv_threads = v1 ? netk::kConvThreads : netk::kConv2Threads;
-    auto conv_kernel = v1 ? netk::k_conv3x3_tc : netk::k_conv3x3_tc2;
+    auto conv_kernel = v1 ? netk::k_conv3x3_tc : (pair ? netk::k_conv3x3_tc2<true> : netk::k_conv3x3_tc2<false>);
     netk::ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.rows_total = net->rows_total;
@@ -412,7 +414,13 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
             net->conv_v1 = env && env[0] == '1';
             cudaDeviceGetAttribute(&net->sm_count, cudaDevAttrMultiProcessorCount, net->cfg.device);
         }
-        net->rows_total = std::max(netk::conv_rows_total(net->geom, n), netk::conv2_rows_total(net->geom, n));
+        {
+            const char* nopair = getenv("DM_NO_PAIR");
+            net->pair_layout = (g == 8) && !net->conv_v1 && !(nopair && nopair[0] == '1');
+        }
+        net->rows_total = net->pair_layout
+                              ? netk::pair_rows_total(n)
+                              : std::max(netk::conv_rows_total(net->geom, n), netk::conv2_rows_total(net->geom, n));
         size_t abytes = (size_t)netk::kChunks * net->rows_total * 16;
         // zeroed once: pad rows are never written afterwards and must stay zero
         DM_TRY(net_alloc_bytes(net, (void**)&net->a0, abytes, true));
@@ -423,8 +431,10 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                true));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv_smem_bytes(net->geom)));
-        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv2_smem_bytes(net->geom)));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::conv2_smem_bytes_pair()));
         DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((27 * C + C + 16 * C) * sizeof(float) + netk::kEncode2Boards * (g + 2) * (g + 2) + 16)));
         DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");

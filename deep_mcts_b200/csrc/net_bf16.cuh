@@ -320,38 +320,72 @@ __global__ void __launch_bounds__(kConvThreads, 1) k_conv3x3_tc(ConvArgs args) {
 // TMEM: accumulator (buf, tile) at column (buf*2 + tile) * 128.
 constexpr int kItemTiles = 2;
 constexpr int kItemRows = kTileM * kItemTiles;  // 256
-constexpr int kStages2 = 2;
+// weight ring: kStages2 stages of kStageK16 K-steps each (one K-step = 16 input channels of one tap
+// = 4 KB; 8 K-steps = one whole tap = 32 KB)
+#ifndef DM_STAGE_K16
+#define DM_STAGE_K16 4
+#endif
+#ifndef DM_STAGES
+#define DM_STAGES 3
+#endif
+constexpr int kStageK16 = DM_STAGE_K16;
+constexpr int kStage2Bytes = kStageK16 * 2 * kC * 16;
+constexpr int kStages2 = DM_STAGES;
+constexpr int kStagesPerTap = (kC / 16) / kStageK16;
 constexpr int kConv2Threads = 224;
 
 __host__ __device__ inline int conv2_a_rows(const RowGeom& geom) { return kItemRows + 2 * geom.halo; }
 inline size_t conv2_smem_bytes(const RowGeom& geom) {
-    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStageBytes + 2 * kC * sizeof(float) +
-           256;
+    return 1024 + (size_t)2 * kChunks * conv2_a_rows(geom) * 16 + (size_t)kStages2 * kStage2Bytes + 2 * kC * sizeof(float) +
+           512;
 }
 inline size_t conv2_rows_total(const RowGeom& geom, int n_boards) {
     size_t body = ((size_t)n_boards * geom.P + kItemRows - 1) / kItemRows * kItemRows;
     return body + 2 * (size_t)geom.halo;
 }
 
+// ---- pad-free layout for 8x8 boards ("pair layout") -------------------------------------------
+// Two boards are interleaved row by row, 9 entries per board row (8 cells + one zero entry):
+//     entry(pair p, line l, board b, x) = kPairFront + ((p*9 + l)*2 + b)*9 + x
+// line 0 of every pair is a zero line (it is also the bottom pad of the previous pair), lines 1..8
+// hold board rows 0..7.  A tap (dy, dx) is a shift of dy*18 + dx entries.  The sixteen 8-row groups
+// (line 1..8) x (board 0, 1) of a pair start 9 entries apart, so ONE tcgen05.mma with stride-byte-offset
+// 144 B covers exactly the 128 real cells of two boards: the zero entries exist in memory but are
+// not rows of the GEMM, which removes the (g+1)^2/g^2 = 1.27x padded rows of the flat layout.
+constexpr int kPairLine = 18;                       // entries per line (2 boards x 9)
+constexpr int kPairEntries = 9 * kPairLine;         // 162 entries per pair
+constexpr int kPairFront = kPairLine;               // zero entries in front of pair 0
+constexpr int kPairItemPairs = 2;                   // one work item = 2 pairs = 4 boards = 2 MMA tiles
+constexpr int kPairARows = kPairItemPairs * kPairEntries + kPairLine + 1;  // 343: + closing pad line + 1 entry in front
+__host__ __device__ inline size_t pair_entry(int board, int y, int x) {
+    return (size_t)kPairFront + ((size_t)((board >> 1) * 9 + 1 + y) * 2 + (board & 1)) * 9 + x;
+}
+inline size_t pair_rows_total(int n_boards) {
+    size_t items = ((size_t)n_boards + 3) / 4;
+    return (size_t)kPairFront + items * kPairItemPairs * kPairEntries + kPairLine + kPairARows;
+}
+inline size_t conv2_smem_bytes_pair() {
+    return 1024 + (size_t)2 * kChunks * kPairARows * 16 + (size_t)kStages2 * kStage2Bytes + 512;
+}
+
 __device__ __forceinline__ void mbar_arrive(u32 bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+template <bool kPair>
 __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args) {
     extern __shared__ unsigned char smem_raw[];
     const RowGeom geom = args.geom;
-    const int a_rows = conv2_a_rows(geom);
+    const int a_rows = kPair ? kPairARows : conv2_a_rows(geom);
     const int live = live_count(args.count_dev, args.n_boards);
-    const int n_items = (int)(((size_t)live * geom.P + kItemRows - 1) / kItemRows);
+    const int n_items = kPair ? (live + 3) / 4 : (int)(((size_t)live * geom.P + kItemRows - 1) / kItemRows);
     if ((int)blockIdx.x >= n_items) return;
 
     unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
     const u32 a_buf_bytes = (u32)kChunks * a_rows * 16;
     unsigned char* s_a = base;                                  // [2][16][a_rows][16 B]
-    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][32 KB]
-    float* s_bias = (float*)(s_b + (size_t)kStages2 * kStageBytes);
-    float* s_vw = s_bias + kC;
-    u64* s_bar = (u64*)(s_vw + kC);
+    unsigned char* s_b = s_a + 2 * (size_t)a_buf_bytes;         // [kStages2][kStage2Bytes]
+    u64* s_bar = (u64*)(s_b + (size_t)kStages2 * kStage2Bytes);
     // barriers: b_full[S], b_empty[S], a_full[2], a_empty[2], acc_full[2], acc_empty[2]
     const u32 bar_bfull = smem_u32(&s_bar[0]), bar_bempty = smem_u32(&s_bar[kStages2]);
     const u32 bar_afull = smem_u32(&s_bar[2 * kStages2]), bar_aempty = smem_u32(&s_bar[2 * kStages2 + 2]);
@@ -362,10 +396,6 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     // below run on the uniform datapath instead of R2UR waterfalls around every UTCHMMA)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x; i < kC; i += blockDim.x) {
-        s_bias[i] = args.bias[i];
-        s_vw[i] = args.vhead_w ? args.vhead_w[i] : 0.f;
-    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; ++s) {
             mbar_init(bar_bfull + 8 * s, 1);
@@ -394,12 +424,13 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
         // ---- weight producer (whole warp runs the loop; one elected lane issues)
         int s = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
-            for (int tap = 0; tap < 9; ++tap, ++s) {
+            for (int part = 0; part < 9 * kStagesPerTap; ++part, ++s) {   // the layer's weights are one contiguous image
                 const int st = s % kStages2;
                 if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
                 if (elect_one()) {
-                    mbar_expect_tx(bar_bfull + 8 * st, kStageBytes);
-                    bulk_g2s(smem_u32(s_b + (size_t)st * kStageBytes), args.w + (size_t)tap * kC * kC, kStageBytes,
+                    mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
+                    bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes),
+                             reinterpret_cast<const unsigned char*>(args.w) + (size_t)part * kStage2Bytes, kStage2Bytes,
                              bar_bfull + 8 * st);
                 }
                 __syncwarp();
@@ -412,7 +443,9 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             const int buf = j & 1;
             if (j >= 2) mbar_wait(bar_aempty + 8 * buf, ((j >> 1) - 1) & 1);
-            const size_t row0 = (size_t)it * kItemRows;
+            // first entry of the item's activation window (pair layout: one entry before the pad line of its first pair)
+            const size_t row0 = kPair ? (size_t)kPairFront + (size_t)it * kPairItemPairs * kPairEntries - 1
+                                      : (size_t)it * kItemRows;
             if (elect_one()) {
                 mbar_expect_tx(bar_afull + 8 * buf, a_chunk_bytes * kChunks);
                 for (int kc = 0; kc < kChunks; ++kc)
@@ -424,41 +457,48 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     } else if (warp == 1) {
         // ---- MMA issuer: the whole warp walks the loop, one elected lane issues each instruction
         const u32 lbo_a = (u32)a_rows * 16, lbo_b = kC * 16;
-        const u32 desc_hi = umma_desc_hi(128);
+        const u32 desc_hi_a = umma_desc_hi(kPair ? 144 : 128);   // pair layout: 8-row groups are 9 entries apart
+        const u32 desc_hi_b = umma_desc_hi(128);
         const u32 a_k16_step = (2 * lbo_a) >> 4, b_k16_step = (2 * lbo_b) >> 4;  // descriptor units (16 B)
+        const u32 a_first = kPair ? (u32)(1 + kPairLine) : (u32)geom.halo;       // first output row within the window
+        const u32 a_tile_step = kPair ? (u32)kPairEntries : (u32)kTileM;
+        const int line = kPair ? kPairLine : geom.Wp;
         int j = 0, s = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             const int buf = j & 1;
             mbar_wait(bar_afull + 8 * buf, (j >> 1) & 1);
             if (j >= 2) mbar_wait(bar_accempty + 8 * buf, ((j >> 1) - 1) & 1);
             tc_fence_after();
-            const u32 a_lo_base = umma_desc_lo(smem_u32(s_a + (size_t)buf * a_buf_bytes), lbo_a) + (u32)geom.halo;
+            const u32 a_lo_base = umma_desc_lo(smem_u32(s_a + (size_t)buf * a_buf_bytes), lbo_a) + a_first;
             const u32 d_base = tmem_base + (u32)(buf * kItemTiles * kC);
-            for (int tap = 0; tap < 9; ++tap, ++s) {
-                const int st = s % kStages2;
-                mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
-                tc_fence_after();
-                const int shift = (tap / 3 - 1) * geom.Wp + (tap % 3 - 1);   // rows == descriptor units
+            for (int tap = 0; tap < 9; ++tap) {
+                const int shift = (tap / 3 - 1) * line + (tap % 3 - 1);   // rows == descriptor units
                 const u32 a_lo_tap = a_lo_base + (u32)shift;
-                const u32 b_lo_tap = umma_desc_lo(smem_u32(s_b + (size_t)st * kStageBytes), lbo_b);
-                if (elect_one()) {
+                for (int part = 0; part < kStagesPerTap; ++part, ++s) {
+                    const int st = s % kStages2;
+                    mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
+                    tc_fence_after();
+                    const u32 b_lo = umma_desc_lo(smem_u32(s_b + (size_t)st * kStage2Bytes), lbo_b);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int tile = 0; tile < kItemTiles; ++tile) {
+                        for (int tile = 0; tile < kItemTiles; ++tile) {
 #pragma unroll
-                        for (int k16 = 0; k16 < kC / 16; ++k16) {
-                            tc_mma_bf16(d_base + (u32)(tile * kC),
-                                        umma_desc_join(a_lo_tap + (u32)(tile * kTileM) + (u32)k16 * a_k16_step, desc_hi),
-                                        umma_desc_join(b_lo_tap + (u32)k16 * b_k16_step, desc_hi), kIdescBf16,
-                                        (tap | k16) ? 1u : 0u);
+                            for (int kk = 0; kk < kStageK16; ++kk) {
+                                const int k16 = part * kStageK16 + kk;
+                                tc_mma_bf16(d_base + (u32)(tile * kC),
+                                            umma_desc_join(a_lo_tap + (u32)tile * a_tile_step + (u32)k16 * a_k16_step, desc_hi_a),
+                                            umma_desc_join(b_lo + (u32)kk * b_k16_step, desc_hi_b), kIdescBf16,
+                                            (tap | k16) ? 1u : 0u);
+                            }
+                        }
+                        tc_commit(bar_bempty + 8 * st);
+                        if (tap == 8 && part == kStagesPerTap - 1) {
+                            tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
+                            tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled
                         }
                     }
-                    tc_commit(bar_bempty + 8 * st);
-                    if (tap == 8) {
-                        tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
-                        tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled
-                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
         }
     } else {
@@ -470,11 +510,26 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
             const int buf = j & 1;
             bool waited = false;
             for (int tile = 0; tile < kItemTiles; ++tile) {
-                const size_t q = (size_t)it * kItemRows + (size_t)tile * kTileM + quarter * 32 + lane;
-                const size_t m = q + geom.halo;
-                const int b = (int)(q / geom.P), rem = (int)(q % geom.P);
-                const int y = rem / geom.Wp, x = rem % geom.Wp;
-                const bool valid = (b < live) && (y < g) && (x < g);
+                size_t m;
+                int b, y, x;
+                bool valid;
+                if (kPair) {
+                    const int r = quarter * 32 + lane;          // accumulator lane = (line, board in pair, x)
+                    const int grp = r >> 3;
+                    x = r & 7;
+                    y = grp >> 1;
+                    b = 2 * (it * kPairItemPairs + tile) + (grp & 1);
+                    m = pair_entry(b, y, x);
+                    valid = b < live;
+                } else {
+                    const size_t q = (size_t)it * kItemRows + (size_t)tile * kTileM + quarter * 32 + lane;
+                    m = q + geom.halo;
+                    b = (int)(q / geom.P);
+                    const int rem = (int)(q % geom.P);
+                    y = rem / geom.Wp;
+                    x = rem % geom.Wp;
+                    valid = (b < live) && (y < g) && (x < g);
+                }
                 // prefetch this row's residual (all 128 channels) before waiting for the tensor core
                 uint4 res[kChunks];
                 if (args.residual && valid) {

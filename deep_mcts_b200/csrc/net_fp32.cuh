@@ -253,7 +253,8 @@ __global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, 
                                                             const u64* first, const u64* second, const u8* player,
                                                             const float* __restrict__ tab,   // [3][27][C]
                                                             const float* __restrict__ basev,  // [2][16][C]
-                                                            int C, __nv_bfloat16* out_bf16, size_t rows_total) {
+                                                            int C, __nv_bfloat16* out_bf16, size_t rows_total,
+                                                            int pair_layout) {
     extern __shared__ __align__(16) float smem[];
     const int g = cfg.g, gp = g + 2, P0 = g * g;
     const int CP = C + 4;                // padded row pitch
@@ -304,7 +305,9 @@ __global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, 
         const float* t1 = s_tab + (1 * 27 + code[gp] + 3 * code[gp + 1] + 9 * code[gp + 2]) * CP;
         const float* t2 = s_tab + (2 * 27 + code[2 * gp] + 3 * code[2 * gp + 1] + 9 * code[2 * gp + 2]) * CP;
         const float* bs = s_base + ((s_player[bb] ? 16 : 0) + cls) * CP;
-        const size_t row = (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
+        // pair layout (8x8 boards, see net_bf16.cuh): rows of two boards interleaved, 9 entries per board row
+        const size_t row = pair_layout ? (size_t)18 + ((size_t)((b >> 1) * 9 + 1 + y) * 2 + (b & 1)) * 9 + x
+                                       : (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
         for (int kc = q; kc < chunks; kc += 4) {
             float a[8];
 #pragma unroll

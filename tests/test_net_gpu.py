@@ -49,7 +49,8 @@ def test_fp32_matches_reference_fixture(golden_dir, name, g, c):
 BF16_SCALES = {"init": (0.577, 0.577), "unit": (1.0, 1.0)}
 
 
-@pytest.mark.parametrize("name,g", [("othello", 8), ("hex", 7), ("hex_with_swap", 7), ("othello", 6), ("hex", 5)])
+@pytest.mark.parametrize("name,g", [("othello", 8), ("hex", 7), ("hex_with_swap", 7), ("othello", 6), ("hex", 5),
+                                    ("hex_with_swap", 8)])
 @pytest.mark.parametrize("scale", ["init", "unit"])
 def test_bf16_tensor_core_path_within_tolerance(name, g, scale):
     game = make_game(name, g)
