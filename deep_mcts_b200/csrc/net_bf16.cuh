@@ -472,7 +472,11 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
             const u32 a_lo_base = umma_desc_lo(smem_u32(s_a + (size_t)buf * a_buf_bytes), lbo_a) + a_first;
             const u32 d_base = tmem_base + (u32)(buf * kItemTiles * kC);
             for (int tap = 0; tap < 9; ++tap) {
+#ifdef DM_EXPERIMENT_ALIGNED
+                const int shift = 8 - (int)a_first;   // timing experiment only: every tap reads a 128-byte aligned window (wrong results)
+#else
                 const int shift = (tap / 3 - 1) * line + (tap % 3 - 1);   // rows == descriptor units
+#endif
                 const u32 a_lo_tap = a_lo_base + (u32)shift;
                 for (int part = 0; part < kStagesPerTap; ++part, ++s) {
                     const int st = s % kStages2;
@@ -530,13 +534,23 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                     x = rem % geom.Wp;
                     valid = (b < live) && (y < g) && (x < g);
                 }
+#ifdef DM_EXP_NOEPI
+                valid = false;   // timing experiment only
+#endif
                 // prefetch this row's residual (all 128 channels) before waiting for the tensor core
                 uint4 res[kChunks];
+#ifdef DM_EXP_NORES
+                if (args.residual && valid) {
+#pragma unroll
+                    for (int kc = 0; kc < kChunks; ++kc) res[kc] = make_uint4(kc, m, kc, m);   // timing experiment: no residual loads
+                }
+#else
                 if (args.residual && valid) {
 #pragma unroll
                     for (int kc = 0; kc < kChunks; ++kc)
                         res[kc] = *reinterpret_cast<const uint4*>(args.residual + ((size_t)kc * args.rows_total + m) * 8);
                 }
+#endif
                 if (!waited) {
                     mbar_wait(bar_accfull + 8 * buf, (j >> 1) & 1);
                     tc_fence_after();
@@ -577,6 +591,10 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                             o.y = pack_bf16(f[c4 * 8 + 2], f[c4 * 8 + 3]);
                             o.z = pack_bf16(f[c4 * 8 + 4], f[c4 * 8 + 5]);
                             o.w = pack_bf16(f[c4 * 8 + 6], f[c4 * 8 + 7]);
+#ifdef DM_EXP_NOSTORE
+                            if (o.x == 0x12345678u && o.y == 0x9abcdef0u)   // timing experiment: keep the math, drop the stores
+#endif
+                            {
                             if (args.out)
                                 *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
                             if (args.out_nhwc)
@@ -586,6 +604,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                                 *reinterpret_cast<uint4*>(
                                     args.out_fc +
                                     ((((size_t)(b >> 7) * P0 + (y * g + x)) * kChunks + (cc * 4 + c4)) * 128 + (b & 127)) * 8) = o;
+                            }
                         }
                     }
                 }
