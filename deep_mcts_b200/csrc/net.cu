@@ -38,6 +38,7 @@ struct dm_net {
     int fc_na = 0, fc_split = 1;
     bool conv_v1 = false;  // DM_CONV_V1=1 selects the non-persistent trunk kernel (A/B testing)
     bool pair_layout = false;  // 8x8 boards: pad-free interleaved layout (DM_NO_PAIR=1 disables, A/B testing)
+    bool fused_blocks = false; // pair layout: one fused kernel per residual block (DM_NO_FUSE=1 disables)
     int sm_count = 148;
     float* fc_partial = nullptr;       // [split][max_batch rounded to 128][NA]
     // activations
@@ -225,7 +226,32 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     a.n_boards = n;
     a.count_dev = count_dev;
     a.geom = net->geom;
-    for (int i = 0; i < R; ++i) {
+    if (net->fused_blocks) {
+        // one fused launch per residual block: conv1 -> T (shared memory) -> conv2 + skip
+        netk::ResBlockArgs ra;
+        memset(&ra, 0, sizeof(ra));
+        ra.x = net->a0;
+        ra.out = net->a0;
+        ra.rows_total = net->rows_total;
+        ra.n_boards = n;
+        ra.count_dev = count_dev;
+        for (int i = 0; i < R; ++i) {
+            ra.w1 = net->trunk_w16[2 * i];
+            ra.w2 = net->trunk_w16[2 * i + 1];
+            memcpy(ra.bias1_c, net->h_trunk_b[2 * i].data(), sizeof(ra.bias1_c));
+            memcpy(ra.bias2_c, net->h_trunk_b[2 * i + 1].data(), sizeof(ra.bias2_c));
+            if (i == R - 1) {
+                ra.vplane = net->vplane;
+                ra.vhead_b = net->vconv_b;
+                memcpy(ra.vw_c, net->h_vconv_w.data(), sizeof(ra.vw_c));
+            }
+            int pc = prof_begin(net, 1, st);
+            netk::k_resblock_tc8<<<conv_blocks, netk::kConv2Threads, netk::resblock_smem_bytes(), st>>>(ra);
+            prof_end(net, pc, st);
+            DM_LAUNCH_CHECK();
+        }
+    }
+    for (int i = 0; i < (net->fused_blocks ? 0 : R); ++i) {
         a.in = net->a0; a.out = net->a1; a.out_nhwc = nullptr; a.residual = nullptr;
         a.w = net->trunk_w16[2 * i]; a.bias = net->trunk_b[2 * i]; a.vhead_w = nullptr; a.vplane = nullptr;
         memcpy(a.bias_c, net->h_trunk_b[2 * i].data(), sizeof(a.bias_c));
@@ -418,6 +444,10 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
             const char* nopair = getenv("DM_NO_PAIR");
             net->pair_layout = (g == 8) && !net->conv_v1 && !(nopair && nopair[0] == '1');
         }
+        {
+            const char* nofuse = getenv("DM_NO_FUSE");
+            net->fused_blocks = net->pair_layout && !(nofuse && nofuse[0] == '1');
+        }
         net->rows_total = net->pair_layout
                               ? netk::pair_rows_total(n)
                               : std::max(netk::conv_rows_total(net->geom, n), netk::conv2_rows_total(net->geom, n));
@@ -435,6 +465,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                      (int)netk::conv2_smem_bytes(net->geom)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv2_smem_bytes_pair()));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc8, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::resblock_smem_bytes()));
         DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((27 * C + C + 16 * C) * sizeof(float) + netk::kEncode2Boards * (g + 2) * (g + 2) + 16)));
         DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");

@@ -624,6 +624,280 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
 }
 
 // ============================================================================================
+// Fused residual block for 8x8 boards (pair layout): one persistent CTA per SM, one work item =
+// 4 whole boards.  Because items are whole boards, the block's intermediate activation T never
+// leaves the SM:
+//     X (global) --bulk copy--> bufX --conv1 (tcgen05)--> acc1 --epilogue 1: +b1, ReLU, bf16--> bufT (smem)
+//     bufT --conv2 (tcgen05)--> acc2 --epilogue 2: +b2, + X (global, L2 hit), ReLU, bf16--> X' (global)
+// (reference ResidualBlock, convolutionalnet.py:109-129).  Compared with two launches of
+// k_conv3x3_tc2 this removes the write and re-read of T, i.e. 2 of the 5 activation passes of a block,
+// which matters because the trunk runs at the board's power cap.  The weight ring streams both
+// layers back to back; conv1 of item j+1 is issued right behind conv2 of item j, so the tensor
+// pipe only idles while epilogue 1 writes T.
+//   TMEM: acc1 = columns 0..255 (2 tiles), acc2 = columns 256..511.
+struct ResBlockArgs {
+    const __nv_bfloat16* x;      // block input, pair layout (also the residual)
+    __nv_bfloat16* out;          // block output, pair layout (may alias x)
+    const __nv_bfloat16* w1;     // [9][16][128][8]
+    const __nv_bfloat16* w2;
+    float vhead_b;
+    float* vplane;               // non-null on the last block: value-head 1x1 conv of the output
+    size_t rows_total;
+    int n_boards;
+    const int* count_dev;
+    float bias1_c[128];
+    float bias2_c[128];
+    float vw_c[128];
+};
+
+inline size_t resblock_smem_bytes() {
+    return 1024 + (size_t)2 * kChunks * kPairARows * 16 + (size_t)kStages2 * kStage2Bytes + 512;
+}
+
+__global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs args) {
+    extern __shared__ unsigned char smem_raw[];
+    const int live = live_count(args.count_dev, args.n_boards);
+    const int n_items = (live + 3) / 4;
+    if ((int)blockIdx.x >= n_items) return;
+
+    unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
+    constexpr u32 kBufBytes = (u32)kChunks * kPairARows * 16;
+    constexpr u32 kLbo = (u32)kPairARows * 16;
+    unsigned char* s_x = base;
+    unsigned char* s_t = s_x + kBufBytes;
+    unsigned char* s_b = s_t + kBufBytes;
+    u64* s_bar = (u64*)(s_b + (size_t)kStages2 * kStage2Bytes);
+    // barriers: b_full[S], b_empty[S], x_full, x_free, acc1_full, t_full, acc2_full, acc2_empty
+    const u32 bar_bfull = smem_u32(&s_bar[0]), bar_bempty = smem_u32(&s_bar[kStages2]);
+    const u32 bar_xfull = smem_u32(&s_bar[2 * kStages2 + 0]), bar_xfree = smem_u32(&s_bar[2 * kStages2 + 1]);
+    const u32 bar_acc1 = smem_u32(&s_bar[2 * kStages2 + 2]), bar_tfull = smem_u32(&s_bar[2 * kStages2 + 3]);
+    const u32 bar_acc2 = smem_u32(&s_bar[2 * kStages2 + 4]), bar_acc2empty = smem_u32(&s_bar[2 * kStages2 + 5]);
+    u32* s_tmem = (u32*)(s_bar + 2 * kStages2 + 8);
+
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int lane = threadIdx.x & 31;
+    // bufT pads must read as zero for conv2: clear it once, the epilogue only ever writes real cells
+    for (u32 i = threadIdx.x; i < kBufBytes / 16; i += blockDim.x)
+        reinterpret_cast<uint4*>(s_t)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(bar_bfull + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, 1);
+        }
+        mbar_init(bar_xfull, 1);
+        mbar_init(bar_xfree, 1);
+        mbar_init(bar_acc1, 1);
+        mbar_init(bar_tfull, 4);      // one arrival per epilogue warp
+        mbar_init(bar_acc2, 1);
+        mbar_init(bar_acc2empty, 4);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill is read by the tensor core
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = *s_tmem;
+
+    if (warp == 0) {
+        // ---- weight producer: layer 1 then layer 2 of every item
+        int s = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+            for (int layer = 0; layer < 2; ++layer) {
+                const unsigned char* w = reinterpret_cast<const unsigned char*>(layer ? args.w2 : args.w1);
+                for (int part = 0; part < 9 * kStagesPerTap; ++part, ++s) {
+                    const int st = s % kStages2;
+                    if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
+                    if (elect_one()) {
+                        mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
+                        bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes), w + (size_t)part * kStage2Bytes, kStage2Bytes,
+                                 bar_bfull + 8 * st);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ---- X producer (single buffer: refilled as soon as conv1 of the previous item has retired)
+        int j = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
+            const size_t row0 = (size_t)kPairFront + (size_t)it * kPairItemPairs * kPairEntries - 1;
+            if (elect_one()) {
+                mbar_expect_tx(bar_xfull, kLbo * kChunks);
+                for (int kc = 0; kc < kChunks; ++kc)
+                    bulk_g2s(smem_u32(s_x + (size_t)kc * kLbo), args.x + ((size_t)kc * args.rows_total + row0) * 8, kLbo,
+                             bar_xfull);
+            }
+            __syncwarp();
+        }
+    } else if (warp == 1) {
+        // ---- MMA issuer
+        const u32 lbo_b = kC * 16;
+        const u32 desc_hi_a = umma_desc_hi(144), desc_hi_b = umma_desc_hi(128);
+        const u32 a_k16_step = (2 * kLbo) >> 4, b_k16_step = (2 * lbo_b) >> 4;
+        const u32 x_lo = umma_desc_lo(smem_u32(s_x), kLbo) + (u32)(1 + kPairLine);
+        const u32 t_lo = umma_desc_lo(smem_u32(s_t), kLbo) + (u32)(1 + kPairLine);
+        int j = 0, s = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            for (int layer = 0; layer < 2; ++layer) {
+                if (layer == 0) {
+                    mbar_wait(bar_xfull, j & 1);
+                } else {
+                    mbar_wait(bar_tfull, j & 1);                              // T of this item is in shared memory
+                    if (j >= 1) mbar_wait(bar_acc2empty, (j - 1) & 1);        // epilogue 2 of the previous item drained acc2
+                }
+                tc_fence_after();
+                const u32 a_lo_base = layer ? t_lo : x_lo;
+                const u32 d_base = tmem_base + (u32)(layer * kItemTiles * kC);
+                for (int tap = 0; tap < 9; ++tap) {
+                    const int shift = (tap / 3 - 1) * kPairLine + (tap % 3 - 1);
+                    const u32 a_lo_tap = a_lo_base + (u32)shift;
+                    for (int part = 0; part < kStagesPerTap; ++part, ++s) {
+                        const int st = s % kStages2;
+                        mbar_wait(bar_bfull + 8 * st, (s / kStages2) & 1);
+                        tc_fence_after();
+                        const u32 b_lo = umma_desc_lo(smem_u32(s_b + (size_t)st * kStage2Bytes), lbo_b);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int tile = 0; tile < kItemTiles; ++tile) {
+#pragma unroll
+                                for (int kk = 0; kk < kStageK16; ++kk) {
+                                    const int k16 = part * kStageK16 + kk;
+                                    tc_mma_bf16(d_base + (u32)(tile * kC),
+                                                umma_desc_join(a_lo_tap + (u32)tile * kPairEntries + (u32)k16 * a_k16_step, desc_hi_a),
+                                                umma_desc_join(b_lo + (u32)kk * b_k16_step, desc_hi_b), kIdescBf16,
+                                                (tap | k16) ? 1u : 0u);
+                                }
+                            }
+                            tc_commit(bar_bempty + 8 * st);
+                            if (tap == 8 && part == kStagesPerTap - 1) {
+                                if (layer == 0) {
+                                    tc_commit(bar_acc1);    // conv1 done: epilogue 1 may start ...
+                                    tc_commit(bar_xfree);   // ... and bufX may take the next item
+                                } else {
+                                    tc_commit(bar_acc2);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    } else {
+        // ---- epilogue warps 3..6
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;   // accumulator lane = (line, board in pair, x)
+        const int grp = r >> 3, x = r & 7, y = grp >> 1;
+        int j = 0;
+        for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            // ---------- epilogue 1: acc1 -> +b1 -> ReLU -> bf16 -> bufT
+            mbar_wait(bar_acc1, j & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int tile = 0; tile < kItemTiles; ++tile) {
+                const u32 widx = (u32)(1 + kPairLine + tile * kPairEntries + grp * 9 + x);   // row inside the window
+                unsigned char* trow = s_t + (size_t)widx * 16;
+#pragma unroll
+                for (int cc = 0; cc < kC / 32; ++cc) {
+                    u32 v[32];
+                    tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)(tile * kC + cc * 32), v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int c4 = 0; c4 < 4; ++c4) {
+                        float f[8];
+#pragma unroll
+                        for (int jj = 0; jj < 8; ++jj)
+                            f[jj] = fmaxf(__uint_as_float(v[c4 * 8 + jj]) + args.bias1_c[cc * 32 + c4 * 8 + jj], 0.f);
+                        uint4 o;
+                        o.x = pack_bf16(f[0], f[1]);
+                        o.y = pack_bf16(f[2], f[3]);
+                        o.z = pack_bf16(f[4], f[5]);
+                        o.w = pack_bf16(f[6], f[7]);
+                        *reinterpret_cast<uint4*>(trow + (size_t)(cc * 4 + c4) * kLbo) = o;
+                    }
+                }
+            }
+            // publish T to the tensor core (generic-proxy writes -> async proxy) and release acc1
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_tfull);
+
+            // ---------- epilogue 2: acc2 -> +b2 + X -> ReLU -> bf16 -> global
+            bool waited = false;
+#pragma unroll 1
+            for (int tile = 0; tile < kItemTiles; ++tile) {
+                const int b = 2 * (it * kPairItemPairs + tile) + (grp & 1);
+                const size_t m = pair_entry(b, y, x);
+                const bool valid = b < live;
+                uint4 res[kChunks];
+                if (valid) {
+#pragma unroll
+                    for (int kc = 0; kc < kChunks; ++kc)
+                        res[kc] = *reinterpret_cast<const uint4*>(args.x + ((size_t)kc * args.rows_total + m) * 8);
+                }
+                if (!waited) {
+                    mbar_wait(bar_acc2, j & 1);
+                    tc_fence_after();
+                    waited = true;
+                }
+                float vacc = 0.f;
+#pragma unroll
+                for (int cc = 0; cc < kC / 32; ++cc) {
+                    u32 v[32];
+                    tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)((kItemTiles + tile) * kC + cc * 32), v);
+                    tc_wait_ld();
+                    if (valid) {
+#pragma unroll
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            const uint4 rr = res[cc * 4 + c4];
+                            const u32 rw[4] = {rr.x, rr.y, rr.z, rr.w};
+                            float f[8];
+#pragma unroll
+                            for (int jj = 0; jj < 4; ++jj) {
+                                f[2 * jj] = __uint_as_float(v[c4 * 8 + 2 * jj]) + args.bias2_c[cc * 32 + c4 * 8 + 2 * jj] +
+                                            __uint_as_float(rw[jj] << 16);
+                                f[2 * jj + 1] = __uint_as_float(v[c4 * 8 + 2 * jj + 1]) +
+                                                args.bias2_c[cc * 32 + c4 * 8 + 2 * jj + 1] +
+                                                __uint_as_float(rw[jj] & 0xffff0000u);
+                            }
+#pragma unroll
+                            for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
+                            if (args.vplane) {
+#pragma unroll
+                                for (int jj = 0; jj < 8; ++jj) vacc = fmaf(f[jj], args.vw_c[cc * 32 + c4 * 8 + jj], vacc);
+                            }
+                            uint4 o;
+                            o.x = pack_bf16(f[0], f[1]);
+                            o.y = pack_bf16(f[2], f[3]);
+                            o.z = pack_bf16(f[4], f[5]);
+                            o.w = pack_bf16(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
+                        }
+                    }
+                }
+                if (valid && args.vplane) args.vplane[(size_t)b * 64 + y * 8 + x] = fmaxf(vacc + args.vhead_b, 0.f);
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acc2empty);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ============================================================================================
 // Policy-head fully connected layer on tcgen05 (reference convolutionalnet.py:146-153):
 //   logits[b][a] = sum_{pos, c} T[b][pos][c] * W[a][c*g*g + pos]
 // as a split-K GEMM: M = 128 boards per tile, N = NA (actions padded to a multiple of 16),
