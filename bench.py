@@ -362,7 +362,8 @@ def run_b200(args):
             "gpu_launches": int(tot_launches),
             "clocks": clock_info,
             "roofline": {
-                "kernel": "k_conv3x3_tc (tcgen05 implicit-GEMM 3x3 conv, 7 launches per round)",
+                "kernel": "k_resblock_tc8 x3 + k_conv3x3_tc2 x1 per round (tcgen05 implicit-GEMM 3x3 convs: three fused "
+                          "residual blocks and the policy conv; seven 128->128 convolutions in four launches)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops if peak_tflops else None,
                 "traffic": ncu_dram_traffic_per_launch() if wl["game"] == "othello" and args.trees == 4096 else None,

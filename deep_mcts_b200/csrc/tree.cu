@@ -159,25 +159,39 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
     if (lane == 0) s_path[0] = node;
     len = 1;
     overflow = false;
-    while (true) {
-        int n = P.n_children[base + node];
-        if (n == 0) break;
-        u32 first = P.first_child[base + node];
-        double sq = sqrt((double)P.visits[base + node]);  // IEEE sqrt, as math.sqrt
-        bool maximise = (s.player == 0);                   // SECOND is the max player (game.py:31-33)
-        double unvisited = maximise ? 0.0 : 1.0;           // parent.player.loss().value (mcts.py:48-50)
+    // header of the current node; below the root it comes out of the parent's child scan, so one
+    // level costs ONE round of (parallel, coalesced) loads instead of a chain of dependent ones
+    int n = P.n_children[base + node];
+    u32 first = P.first_child[base + node];
+    u32 parent_visits = P.visits[base + node];
+    while (n != 0) {
+        double sq = sqrt((double)parent_visits);      // IEEE sqrt, as math.sqrt
+        bool maximise = (s.player == 0);              // SECOND is the max player (game.py:31-33)
+        double unvisited = maximise ? 0.0 : 1.0;      // parent.player.loss().value (mcts.py:48-50)
         double best_key = 0.0;
         int best = -1;
+        // whole record of this lane's best child
+        u32 b_visits = 0, b_first = 0;
+        int b_n = 0, b_action = 0;
         for (int j = lane; j < n; j += 32) {
             size_t c = base + first + j;
             u32 v = P.visits[c];
-            double value = (v == 0) ? unvisited : __ddiv_rn(P.value_sum[c], (double)v);
+            double vs = P.value_sum[c];
+            double pr = P.prior[c];
+            u32 cf = P.first_child[c];
+            int cn = P.n_children[c];
+            int ca = P.action[c];
+            double value = (v == 0) ? unvisited : __ddiv_rn(vs, (double)v);
             // u = ((c_puct * P) * sqrt(N)) / (1 + n)   (mcts.py:40-43), no FMA contraction
-            double u = __ddiv_rn(__dmul_rn(__dmul_rn(P.c_puct, P.prior[c]), sq), (double)(1u + v));
+            double u = __ddiv_rn(__dmul_rn(__dmul_rn(P.c_puct, pr), sq), (double)(1u + v));
             double key = maximise ? __dadd_rn(value, u) : -__dsub_rn(value, u);
             if (best < 0 || key > best_key) {
                 best_key = key;
                 best = j;
+                b_visits = v;
+                b_first = cf;
+                b_n = cn;
+                b_action = ca;
             }
         }
 #pragma unroll
@@ -189,15 +203,23 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
                 best = ob;
             }
         }
+        // the winning child was scanned by lane (best & 31), whose local best it is
+        const int owner = best & 31;
+        parent_visits = __shfl_sync(DM_FULL_MASK, b_visits, owner);
+        const u32 next_first = __shfl_sync(DM_FULL_MASK, b_first, owner);
+        const int next_n = __shfl_sync(DM_FULL_MASK, b_n, owner);
+        const int act = __shfl_sync(DM_FULL_MASK, b_action, owner);
         scanned += (unsigned long long)n;
         node = first + (u32)best;
-        s = game_child(P.cfg, s, P.action[base + node]);
+        s = game_child(P.cfg, s, act);
         if (len >= DM_MAX_DEPTH) {
             overflow = true;
             break;
         }
         if (lane == 0) s_path[len] = node;
         ++len;
+        first = next_first;
+        n = next_n;
     }
     __syncwarp();
     return len;
@@ -665,27 +687,21 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
         Philox rng;
         rng.init(P.seed, (u32)t, 0x6d6f7665u, P.rng_ctr[t]);
         u32 r = rng.below(total);
-        // order children by action id so the draw is a function of (r, visits by action)
-        chosen = -1;
-        u32 acc_best = 0xffffffffu;
-        for (int k = 0, j = lane; j < n; j += 32, ++k) {
-            // cumulative visits of all children with action id <= a[k]
-            u32 cum = 0;
-            for (int jj = 0; jj < n; ++jj)
-                if (P.action[base + first + jj] <= a[k]) cum += P.visits[base + first + jj];
-            if (v[k] > 0 && cum > r && cum < acc_best) {
-                acc_best = cum;
-                chosen = a[k];
-            }
-        }
+        // inverse CDF over the children in child order (any fixed order gives the same distribution;
+        // the device stream is Philox, not numpy's, so only the distribution is comparable anyway)
+        u32 run = 0;
+        for (int k = 0, j0 = 0; j0 < n && chosen < 0; j0 += 32, ++k) {
+            u32 vk = (j0 + lane < n) ? v[k] : 0u;
+            u32 incl = vk;
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            u32 ob = __shfl_xor_sync(DM_FULL_MASK, acc_best, off);
-            int oc = __shfl_xor_sync(DM_FULL_MASK, chosen, off);
-            if (ob < acc_best) {
-                acc_best = ob;
-                chosen = oc;
+            for (int off = 1; off < 32; off <<= 1) {
+                u32 up = __shfl_up_sync(DM_FULL_MASK, incl, off);
+                if (lane >= off) incl += up;
             }
+            bool pick = vk > 0 && r >= run + incl - vk && r < run + incl;
+            u32 m = __ballot_sync(DM_FULL_MASK, pick);
+            if (m) chosen = __shfl_sync(DM_FULL_MASK, a[k], __ffs(m) - 1);
+            run += __shfl_sync(DM_FULL_MASK, incl, 31);
         }
         if (lane == 0) P.rng_ctr[t] += 1;
     }
