@@ -164,8 +164,8 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
     int n = P.n_children[base + node];
     u32 first = P.first_child[base + node];
     u32 parent_visits = P.visits[base + node];
+    double sq = sqrt((double)parent_visits);          // IEEE sqrt, as math.sqrt
     while (n != 0) {
-        double sq = sqrt((double)parent_visits);      // IEEE sqrt, as math.sqrt
         bool maximise = (s.player == 0);              // SECOND is the max player (game.py:31-33)
         double unvisited = maximise ? 0.0 : 1.0;      // parent.player.loss().value (mcts.py:48-50)
         double best_key = 0.0;
@@ -173,39 +173,62 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
         // whole record of this lane's best child
         u32 b_visits = 0, b_first = 0;
         int b_n = 0, b_action = 0;
-        for (int j = lane; j < n; j += 32) {
-            size_t c = base + first + j;
-            u32 v = P.visits[c];
-            double vs = P.value_sum[c];
-            double pr = P.prior[c];
-            u32 cf = P.first_child[c];
-            int cn = P.n_children[c];
-            int ca = P.action[c];
-            double value = (v == 0) ? unvisited : __ddiv_rn(vs, (double)v);
+        // children lane and lane + 32 are loaded together so their divisions overlap; a third
+        // (only Hex-with-swap 8x8 has 65 actions) takes the loop again
+        for (int j0 = lane; j0 < n; j0 += 64) {
+            const int j1 = j0 + 32;
+            const bool has1 = j1 < n;
+            size_t c0 = base + first + j0, c1 = has1 ? c0 + 32 : c0;
+            u32 v0 = P.visits[c0], v1 = P.visits[c1];
+            double vs0 = P.value_sum[c0], vs1 = P.value_sum[c1];
+            double pr0 = P.prior[c0], pr1 = P.prior[c1];
+            u32 cf0 = P.first_child[c0], cf1 = P.first_child[c1];
+            int cn0 = P.n_children[c0], cn1 = P.n_children[c1];
+            int ca0 = P.action[c0], ca1 = P.action[c1];
+            double q0 = (v0 == 0) ? unvisited : __ddiv_rn(vs0, (double)v0);
+            double q1 = (v1 == 0) ? unvisited : __ddiv_rn(vs1, (double)v1);
             // u = ((c_puct * P) * sqrt(N)) / (1 + n)   (mcts.py:40-43), no FMA contraction
-            double u = __ddiv_rn(__dmul_rn(__dmul_rn(P.c_puct, pr), sq), (double)(1u + v));
-            double key = maximise ? __dadd_rn(value, u) : -__dsub_rn(value, u);
-            if (best < 0 || key > best_key) {
-                best_key = key;
-                best = j;
-                b_visits = v;
-                b_first = cf;
-                b_n = cn;
-                b_action = ca;
+            double u0 = __ddiv_rn(__dmul_rn(__dmul_rn(P.c_puct, pr0), sq), (double)(1u + v0));
+            double u1 = __ddiv_rn(__dmul_rn(__dmul_rn(P.c_puct, pr1), sq), (double)(1u + v1));
+            // "+ 0.0" folds -0.0 into +0.0 so the integer comparison below orders like the doubles
+            double k0 = (maximise ? __dadd_rn(q0, u0) : -__dsub_rn(q0, u0)) + 0.0;
+            double k1 = (maximise ? __dadd_rn(q1, u1) : -__dsub_rn(q1, u1)) + 0.0;
+            if (best < 0 || k0 > best_key) {
+                best_key = k0;
+                best = j0;
+                b_visits = v0;
+                b_first = cf0;
+                b_n = cn0;
+                b_action = ca0;
+            }
+            if (has1 && k1 > best_key) {
+                best_key = k1;
+                best = j1;
+                b_visits = v1;
+                b_first = cf1;
+                b_n = cn1;
+                b_action = ca1;
             }
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            double ok = __shfl_xor_sync(DM_FULL_MASK, best_key, off);
-            int ob = __shfl_xor_sync(DM_FULL_MASK, best, off);
-            if (ob >= 0 && (best < 0 || ok > best_key || (ok == best_key && ob < best))) {
-                best_key = ok;
-                best = ob;
-            }
+        // sqrt for the next level, off the critical path of the reduction below
+        const double b_sq = sqrt((double)b_visits);
+        // warp arg-max (first extremum wins): order-preserving integer image of the key, reduced
+        // with three redux.sync instead of five shuffle rounds
+        unsigned long long kb = 0;
+        if (best >= 0) {
+            unsigned long long bits = (unsigned long long)__double_as_longlong(best_key);
+            kb = (bits >> 63) ? ~bits : (bits | 0x8000000000000000ull);
         }
+        const u32 hi = (u32)(kb >> 32), lo = (u32)kb;
+        const u32 mh = __reduce_max_sync(DM_FULL_MASK, hi);
+        bool cand = hi == mh;
+        const u32 ml = __reduce_max_sync(DM_FULL_MASK, cand ? lo : 0u);
+        cand = cand && lo == ml;
+        best = (int)__reduce_min_sync(DM_FULL_MASK, cand ? (u32)best : 0xffffffffu);
         // the winning child was scanned by lane (best & 31), whose local best it is
         const int owner = best & 31;
         parent_visits = __shfl_sync(DM_FULL_MASK, b_visits, owner);
+        sq = __shfl_sync(DM_FULL_MASK, b_sq, owner);
         const u32 next_first = __shfl_sync(DM_FULL_MASK, b_first, owner);
         const int next_n = __shfl_sync(DM_FULL_MASK, b_n, owner);
         const int act = __shfl_sync(DM_FULL_MASK, b_action, owner);
@@ -777,6 +800,8 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
 // --------------------------------------------------- kernel: external-evaluator select
 // 7 blocks x 4 warps = 28 warps per SM: 148 SMs hold 4144 trees in ONE wave (ncu showed 1.15
 // waves at 80 registers, i.e. a nearly empty second pass over a latency-bound kernel).
+constexpr int kLevelBudget = 32;
+
 template <bool kSelfPlay>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
     __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
@@ -799,6 +824,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
     u8 flags = P.flags[t];
     u32 without = P.stat_without[t];
     bool emitted = false;
+    int levels = 0;
     while (sims > 0) {
         u32 root = P.root[t];
         GState s;
@@ -831,6 +857,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
                 ++terminal;
                 ++done;
                 --sims;
+                // The launch lasts as long as its slowest warp.  A self-play tree that has already
+                // walked kLevelBudget levels sits this round out instead of descending again (its
+                // result does not depend on which round a simulation runs in); a stepped search
+                // keeps going because its caller counts rounds.
+                levels += len - 1;
+                if (kSelfPlay && levels + (len - 1) > kLevelBudget) break;
                 continue;
             }
         }
