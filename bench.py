@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
+    ap.add_argument("--pool-sizes", type=str, default="", help="comma-separated games per pool (default: even split)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay a captured CUDA graph of the round")
     return ap.parse_args()
 
@@ -203,8 +204,9 @@ def run_b200(args):
     net.max_batch = args.trees
     sims, T = wl["num_simulations"], args.trees
     engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
-                             replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools)
-    engine.use_graph = bool(args.graph) and args.pools == 1
+                             replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools,
+                             pool_sizes=[int(x) for x in args.pool_sizes.split(",")] if args.pool_sizes else None)
+    engine.use_graph = bool(args.graph)
     dn = net.device_net()   # e2e leg (full-width batches)
     lib = _lib.load()
 

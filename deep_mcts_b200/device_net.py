@@ -164,6 +164,12 @@ class DeviceNet:
             timers.append(("select", ev[0], ev[1]))
             timers.append(("expand_backup", ev[2], ev[3]))
 
+    def evaluate_pending(self, pool) -> None:
+        """Network evaluation + expand/backup of the leaves a previous select left pending."""
+        value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity,
+                                            pool.leaf_count)
+        pool.expand_backup(probs, value)
+
     def run_search(self, pool, sims: int) -> None:
         """All armed simulations of one MCTS.step.  Exact mode: at most sims + 1 rounds (root
         expansion), no host synchronisation.  Virtual-loss mode: rounds until no tree hands out a leaf."""

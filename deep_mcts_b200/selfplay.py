@@ -8,7 +8,7 @@ every new root, subtree reuse, outcome labelling of the recorded positions, imme
 -- and every search round evaluates one leaf per tree in a single network batch.  There is no
 host synchronisation inside ``run_rounds``.
 """
-from typing import Optional, Tuple
+from typing import Optional, Sequence, Tuple
 
 import torch
 
@@ -20,18 +20,26 @@ from .pool import TreePool, default_node_capacity
 class BatchedSelfPlay:
     def __init__(self, net, n_trees: int, num_simulations: int, sample_move_cutoff: int = 0,
                  dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, replay_capacity: int = 1 << 20,
-                 seed: int = 0, max_nodes_per_tree: Optional[int] = None, n_pools: int = 1) -> None:
+                 seed: int = 0, max_nodes_per_tree: Optional[int] = None, n_pools: int = 1,
+                 pool_sizes: Optional[Sequence[int]] = None) -> None:
         """``net`` is a GameNet (its weights are used) or a DeviceNet.
 
         ``n_pools`` > 1 splits the games into independent pools, each with its own network
         buffers and CUDA stream.  The pools' rounds are dependency chains of their own, so the
         latency-bound tree kernels of one pool run under the tensor-bound network kernels of
-        another (no collective, no data shared between pools)."""
-        if n_trees % n_pools:
-            raise ValueError("n_trees must be divisible by n_pools")
+        another (no collective, no data shared between pools).  ``pool_sizes`` gives the games per
+        pool explicitly (default: an even split); sizes that are multiples of 4 x the SM count
+        keep every trunk launch at whole waves of work items."""
+        if pool_sizes is None:
+            if n_trees % n_pools:
+                raise ValueError("n_trees must be divisible by n_pools")
+            pool_sizes = [n_trees // n_pools] * n_pools
+        pool_sizes = [int(x) for x in pool_sizes]
+        if len(pool_sizes) != n_pools or sum(pool_sizes) != n_trees or min(pool_sizes) <= 0:
+            raise ValueError("pool_sizes must be n_pools positive sizes that add up to n_trees")
         self.net = net
         manager = net.manager
-        per_pool = n_trees // n_pools
+        self.pool_sizes = pool_sizes
         cap = max_nodes_per_tree or default_node_capacity(manager, num_simulations)
         self.num_simulations = num_simulations
         self.n_trees = n_trees
@@ -39,33 +47,34 @@ class BatchedSelfPlay:
         self.pools = []
         self.device_nets = []
         for i in range(n_pools):
-            pool = TreePool(manager, per_pool, cap, seed=seed * 1000 + i)
+            pool = TreePool(manager, pool_sizes[i], cap, seed=seed * 1000 + i)
             pool.configure(num_simulations, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, sample_move_cutoff,
                            dirichlet_alpha, dirichlet_factor)
-            pool.enable_selfplay(max(1, replay_capacity // n_pools))
+            pool.enable_selfplay(max(1, replay_capacity * pool_sizes[i] // n_trees))
             self.pools.append(pool)
         if isinstance(net, DeviceNet):
             if n_pools != 1:
                 raise ValueError("pass a GameNet when n_pools > 1 (each pool needs its own network buffers)")
-            if net.max_batch < per_pool:
+            if net.max_batch < pool_sizes[0]:
                 raise ValueError("DeviceNet.max_batch must be >= trees per pool")
             self.device_nets = [net]
         else:
-            self._build_device_nets(per_pool)
+            self._build_device_nets()
         self.pool = self.pools[0]
         self.tree_timers = None     # set to a list to collect CUDA-event pairs around the tree kernels
         self.use_graph = False      # set True to replay one captured round instead of re-launching it
         self._graph = None
+        self._phase_offset = False  # pools[1:] hold a pending selection (pipelined graph mode)
         self._graph_launches = 0
         self.graph_replays = 0
         self.streams = [torch.cuda.Stream(device=self.pool.device) for _ in range(n_pools)] if n_pools > 1 else [None]
 
-    def _build_device_nets(self, per_pool: int) -> None:
+    def _build_device_nets(self) -> None:
         net = self.net
         sd = net.net.state_dict()
         self.device_nets = []
-        for _ in range(self.n_pools):
-            dn = DeviceNet(net.manager, net.channels, net.num_residual, net.value_head_hidden_units, per_pool,
+        for size in self.pool_sizes:
+            dn = DeviceNet(net.manager, net.channels, net.num_residual, net.value_head_hidden_units, size,
                            net.precision)
             dn.load_state_dict(sd)
             self.device_nets.append(dn)
@@ -91,6 +100,21 @@ class BatchedSelfPlay:
             for _ in range(int(rounds)):
                 dn.search_round(pool, selfplay=True, timers=self.tree_timers)
             return
+        if self.use_graph:
+            if self._graph is None:
+                self._capture_pipelined_round()
+            if not self._phase_offset:
+                for pool in self.pools[1:]:
+                    pool.selfplay_select()          # prime the phase offset: a selection is pending
+                self._phase_offset = True
+            for _ in range(int(rounds)):
+                self._graph.replay()
+            self.graph_replays += int(rounds)
+            return
+        if self._phase_offset:
+            for dn, pool in zip(self.device_nets[1:], self.pools[1:]):
+                dn.evaluate_pending(pool)           # finish the round the graph left half done
+            self._phase_offset = False
         current = torch.cuda.current_stream()
         for st in self.streams:
             st.wait_stream(current)
@@ -102,7 +126,7 @@ class BatchedSelfPlay:
             current.wait_stream(st)
 
     def _capture_round(self) -> None:
-        """Capture one select -> network -> expand/backup round (13 kernel launches + 1 memset) into a
+        """Capture one select -> network -> expand/backup round (kernel launches + 1 memset) into a
         CUDA graph; the round has no host-visible state, so replaying it is identical to launching it."""
         dn, pool = self.device_nets[0], self.pools[0]
         dn.search_round(pool, selfplay=True)        # warm every kernel outside the capture
@@ -112,6 +136,33 @@ class BatchedSelfPlay:
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             dn.search_round(pool, selfplay=True)
+        self._graph_launches = int(lib.dm_launch_count() - before)
+        self._graph = graph
+
+    def _capture_pipelined_round(self) -> None:
+        """One graph with a branch per pool.  Pool 0's branch is select -> network -> expand/backup;
+        the other pools run a phase apart, network -> expand/backup -> select (their selection for
+        the next replay), so a pool's tree kernels are in flight while another pool's trunk
+        occupies the tensor cores.  Every pool still does exactly one round per replay."""
+        for dn, pool in zip(self.device_nets, self.pools):
+            dn.search_round(pool, selfplay=True)    # warm every kernel outside the capture
+        torch.cuda.synchronize()
+        lib = _lib.load()
+        before = lib.dm_launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            current = torch.cuda.current_stream()
+            for st in self.streams:
+                st.wait_stream(current)
+            for i, (dn, pool, st) in enumerate(zip(self.device_nets, self.pools, self.streams)):
+                with torch.cuda.stream(st):
+                    if i == 0:
+                        dn.search_round(pool, selfplay=True)
+                    else:
+                        dn.evaluate_pending(pool)
+                        pool.selfplay_select()
+            for st in self.streams:
+                current.wait_stream(st)
         self._graph_launches = int(lib.dm_launch_count() - before)
         self._graph = graph
 

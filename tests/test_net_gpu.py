@@ -179,3 +179,73 @@ def test_mcts_with_policy_network_rollouts_matches_oracle():
             a = int(np.argmax(ref_dist))
             m.advance(a)
             ref.advance(a)
+
+
+def test_config1_tictactoe_net_search_exact_over_100_games():
+    """BASELINE config 1: TicTacToeManager + ConvolutionalTicTacToeNet() (C=3, R=3, H=128) with
+    torch.manual_seed(0) weights, 25 simulations, alpha = 0, cutoff 0, 100 games that differ by a
+    forced random opening; every move's visit counts are compared.  The oracle search is fed the
+    device network's own outputs (evaluated one state at a time), so the comparison is exact: it
+    pins net -> priors -> expansion -> PUCT plumbing and that a board's result does not depend on
+    its position in the batch.  The device outputs themselves are checked against the torch-fp32
+    oracle net within 1e-5."""
+    from deep_mcts_b200 import mcts as dm
+    from deep_mcts_b200.gamenet import cached_state_evaluator
+    from deep_mcts_b200.tictactoe.convolutionalnet import ConvolutionalTicTacToeNet
+    from oracle.mcts import OracleMCTS
+    torch.manual_seed(0)
+    net = ConvolutionalTicTacToeNet()
+    net.precision = "fp32"
+    net.max_batch = 128
+    sd = {k: v.detach().cpu() for k, v in net.net.state_dict().items()}
+    game = make_game("tictactoe", 3)
+    manager = net.manager
+    dn = net.device_net()
+    cache = {}
+
+    def device_outputs(g, state):
+        hit = cache.get(state)
+        if hit is None:
+            v, p = dn.evaluate([state[0]], [state[1]], [state[2]])
+            want_v, want_p = onet.evaluate_batch(g, sd, [state])
+            assert abs(float(v[0]) - float(want_v[0])) < FP32_ATOL
+            np.testing.assert_allclose(p[0][:9], want_p[0], atol=FP32_ATOL, rtol=0)
+            hit = (float(v[0]), [float(x) for x in p[0][:9]])
+            cache[state] = hit
+        return hit
+
+    T, sims = 100, 25
+    rs = np.random.RandomState(0)
+    openings = []
+    for _ in range(T):
+        s = game.initial_state()
+        for _ in range(rs.randint(0, 3)):
+            legal = game.legal_list(s)
+            s = game.child(s, legal[rs.randint(len(legal))])
+        openings.append(s)
+    batch = dm.BatchedMCTS(manager, T, sims, None, cached_state_evaluator(net))
+    batch.pool.set_root_states(np.array([o[0] for o in openings], np.uint8),
+                               np.array([o[1] for o in openings], np.uint64),
+                               np.array([o[2] for o in openings], np.uint64))
+    refs = []
+    for o in openings:
+        r = OracleMCTS(game, sims, None, device_outputs)
+        r.set_root_state(o)
+        refs.append(r)
+    live = np.ones(T, bool)
+    moves = 0
+    while live.any():
+        visits, stats = batch.step(tree_ids=np.where(live)[0].astype(np.int32))
+        actions = np.full(T, -1, np.int32)
+        for t in np.where(live)[0]:
+            _, ref_stats = refs[t].step()
+            assert [int(v) for v in visits[t]][:9] == refs[t].root_visit_counts()[:9], (t, moves)
+            assert tuple(stats[t]) == tuple(ref_stats)
+            a = int(np.argmax(visits[t]))
+            refs[t].advance(a)
+            actions[t] = a
+            moves += 1
+            if game.is_final(refs[t].state):
+                live[t] = False
+        batch.advance(actions)
+    assert moves > 500 and batch.pool.counters()["capacity_errors"] == 0

@@ -97,6 +97,35 @@ def test_selfplay_with_device_net_runs_and_labels_consistently():
     assert engine2.counters()["games"] > 10
 
 
+def test_pipelined_pool_graph_accounting():
+    """Uneven pools replayed as one two-branch CUDA graph (pool 1 runs a phase behind pool 0): every
+    replay is one round per pool, simulations are counted once, and switching between the graph and
+    launch-by-launch modes completes the half-done round instead of expanding a leaf twice."""
+    from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
+    from deep_mcts_b200.selfplay import BatchedSelfPlay
+    torch.manual_seed(0)
+    net = ConvolutionalOthelloNet(4)
+    sims = 8
+    engine = BatchedSelfPlay(net, 96, sims, sample_move_cutoff=4, dirichlet_alpha=1.0, replay_capacity=1 << 14,
+                             seed=5, n_pools=2, pool_sizes=[64, 32])
+    engine.use_graph = True
+    engine.run_rounds(90)
+    engine.use_graph = False
+    engine.run_rounds(9)
+    engine.use_graph = True
+    engine.run_rounds(90)
+    torch.cuda.synchronize()
+    c = engine.counters()
+    assert c["capacity_errors"] == 0 and c["games"] > 20
+    assert c["simulations"] > 0.8 * 96 * 180      # a round is at least one simulation for (nearly) every tree
+    # every finished move took exactly `sims` simulations; at most one move per tree is in progress
+    assert c["moves"] * sims <= c["simulations"] <= (c["moves"] + 96) * sims
+    for pool in engine.pools:
+        n = min(int(pool.replay_written.item()), pool.replay_capacity)
+        pi = pool.replay_pi[:n, :17].cpu().numpy()
+        np.testing.assert_allclose(pi.sum(axis=1), 1.0, atol=1e-5)
+
+
 def test_weight_transfer_keeps_graph_valid_and_changes_outputs():
     """Re-packing weights (the reference's weight transfer, train.py:169-171) must update the kernels'
     weights in place: outputs follow the new weights and a captured CUDA graph of the round stays valid."""
