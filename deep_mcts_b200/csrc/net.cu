@@ -38,7 +38,7 @@ struct dm_net {
     int fc_na = 0, fc_split = 1;
     bool conv_v1 = false;  // DM_CONV_V1=1 selects the non-persistent trunk kernel (A/B testing)
     bool pair_layout = false;  // 8x8 boards: pad-free interleaved layout (DM_NO_PAIR=1 disables, A/B testing)
-    bool fused_blocks = false; // pair layout: one fused kernel per residual block (DM_NO_FUSE=1 disables)
+    bool fused_blocks = false; // g = 8 / g = 7: one fused kernel per residual block (DM_NO_FUSE=1 disables)
     int sm_count = 148;
     float* fc_partial = nullptr;       // [split][max_batch rounded to 128][NA]
     // activations
@@ -246,7 +246,10 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
                 memcpy(ra.vw_c, net->h_vconv_w.data(), sizeof(ra.vw_c));
             }
             int pc = prof_begin(net, 1, st);
-            netk::k_resblock_tc8<<<conv_blocks, netk::kConv2Threads, netk::resblock_smem_bytes(), st>>>(ra);
+            if (g.g == 8)
+                netk::k_resblock_tc<8><<<conv_blocks, netk::kConv2Threads, netk::resblock_smem_bytes<8>(), st>>>(ra);
+            else
+                netk::k_resblock_tc<7><<<conv_blocks, netk::kConv2Threads, netk::resblock_smem_bytes<7>(), st>>>(ra);
             prof_end(net, pc, st);
             DM_LAUNCH_CHECK();
         }
@@ -446,7 +449,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
         }
         {
             const char* nofuse = getenv("DM_NO_FUSE");
-            net->fused_blocks = net->pair_layout && !(nofuse && nofuse[0] == '1');
+            // whole-board work items: 8x8 in the pair layout, 7x7 in the flat layout (64 rows per board)
+            net->fused_blocks = (net->pair_layout || (g == 7 && !net->conv_v1)) && !(nofuse && nofuse[0] == '1');
         }
         net->rows_total = net->pair_layout
                               ? netk::pair_rows_total(n)
@@ -465,8 +469,10 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                      (int)netk::conv2_smem_bytes(net->geom)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv2_smem_bytes_pair()));
-        DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc8, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)netk::resblock_smem_bytes()));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::resblock_smem_bytes<8>()));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::resblock_smem_bytes<7>()));
         DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((27 * C + C + 16 * C) * sizeof(float) + netk::kEncode2Boards * (g + 2) * (g + 2) + 16)));
         DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");

@@ -624,9 +624,10 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
 }
 
 // ============================================================================================
-// Fused residual block for 8x8 boards (pair layout): one persistent CTA per SM, one work item =
-// 4 whole boards.  Because items are whole boards, the block's intermediate activation T never
-// leaves the SM:
+// Fused residual block for boards whose work items are whole boards: 8x8 in the pair layout and
+// 7x7 in the flat layout (P = 64 rows per board, so a 256-row item is exactly 4 boards).  One
+// persistent CTA per SM, one work item = 4 boards.  Because items are whole boards, the block's
+// intermediate activation T never leaves the SM:
 //     X (global) --bulk copy--> bufX --conv1 (tcgen05)--> acc1 --epilogue 1: +b1, ReLU, bf16--> bufT (smem)
 //     bufT --conv2 (tcgen05)--> acc2 --epilogue 2: +b2, + X (global, L2 hit), ReLU, bf16--> X' (global)
 // (reference ResidualBlock, convolutionalnet.py:109-129).  Compared with two launches of
@@ -635,9 +636,60 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
 // layers back to back; conv1 of item j+1 is issued right behind conv2 of item j, so the tensor
 // pipe only idles while epilogue 1 writes T.
 //   TMEM: acc1 = columns 0..255 (2 tiles), acc2 = columns 256..511.
+// Geometry of the two instantiations.  G = 8: pair layout (no pad rows in the GEMM).  G = 7: flat
+// rows with Wp = 8; a board's pad column and pad line are rows of the GEMM whose results are
+// dropped, and every halo row a real cell reads is a pad of its own or the previous board.
+template <int G>
+struct ResGeom;
+template <>
+struct ResGeom<8> {
+    static constexpr int kWinRows = kPairARows;          // rows of the activation window in shared memory
+    static constexpr int kFirst = 1 + kPairLine;         // first output row inside the window
+    static constexpr int kTileStep = kPairEntries;       // window rows between the item's two MMA tiles
+    static constexpr int kSbo = 144;                     // bytes between 8-row groups
+    static constexpr int kLine = kPairLine;              // window rows per dy
+    __device__ static size_t window_row0(int it) { return (size_t)kPairFront + (size_t)it * kPairItemPairs * kPairEntries - 1; }
+};
+template <>
+struct ResGeom<7> {
+    static constexpr int kWinRows = kItemRows + 2 * 9;
+    static constexpr int kFirst = 9;
+    static constexpr int kTileStep = kTileM;
+    static constexpr int kSbo = 128;
+    static constexpr int kLine = 8;
+    __device__ static size_t window_row0(int it) { return (size_t)it * kItemRows; }
+};
+// accumulator row (tile, r = TMEM lane) of item `it` -> board, cell, window row, global row
+template <int G>
+struct ResRow {
+    int b, y, x;
+    u32 widx;
+    size_t m;
+    bool cell;   // a real board cell (always true in the pair layout)
+    __device__ ResRow(int it, int tile, int r) {
+        if (G == 8) {
+            const int grp = r >> 3;
+            x = r & 7;
+            y = grp >> 1;
+            b = 2 * (it * kPairItemPairs + tile) + (grp & 1);
+            widx = (u32)(1 + kPairLine + tile * kPairEntries + grp * 9 + x);
+            m = pair_entry(b, y, x);
+            cell = true;
+        } else {
+            const int q = tile * kTileM + r;
+            x = q & 7;
+            y = (q >> 3) & 7;
+            b = it * 4 + (q >> 6);
+            widx = (u32)(9 + q);
+            m = (size_t)it * kItemRows + q + 9;
+            cell = (x < 7) && (y < 7);
+        }
+    }
+};
+
 struct ResBlockArgs {
-    const __nv_bfloat16* x;      // block input, pair layout (also the residual)
-    __nv_bfloat16* out;          // block output, pair layout (may alias x)
+    const __nv_bfloat16* x;      // block input (also the residual)
+    __nv_bfloat16* out;          // block output, same layout (may alias x)
     const __nv_bfloat16* w1;     // [9][16][128][8]
     const __nv_bfloat16* w2;
     float vhead_b;
@@ -650,19 +702,22 @@ struct ResBlockArgs {
     float vw_c[128];
 };
 
+template <int G>
 inline size_t resblock_smem_bytes() {
-    return 1024 + (size_t)2 * kChunks * kPairARows * 16 + (size_t)kStages2 * kStage2Bytes + 512;
+    return 1024 + (size_t)2 * kChunks * ResGeom<G>::kWinRows * 16 + (size_t)kStages2 * kStage2Bytes + 512;
 }
 
-__global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs args) {
+template <int G>
+__global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs args) {
+    using Geo = ResGeom<G>;
     extern __shared__ unsigned char smem_raw[];
     const int live = live_count(args.count_dev, args.n_boards);
     const int n_items = (live + 3) / 4;
     if ((int)blockIdx.x >= n_items) return;
 
     unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
-    constexpr u32 kBufBytes = (u32)kChunks * kPairARows * 16;
-    constexpr u32 kLbo = (u32)kPairARows * 16;
+    constexpr u32 kBufBytes = (u32)kChunks * Geo::kWinRows * 16;
+    constexpr u32 kLbo = (u32)Geo::kWinRows * 16;
     unsigned char* s_x = base;
     unsigned char* s_t = s_x + kBufBytes;
     unsigned char* s_b = s_t + kBufBytes;
@@ -727,7 +782,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
         int j = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
-            const size_t row0 = (size_t)kPairFront + (size_t)it * kPairItemPairs * kPairEntries - 1;
+            const size_t row0 = Geo::window_row0(it);
             if (elect_one()) {
                 mbar_expect_tx(bar_xfull, kLbo * kChunks);
                 for (int kc = 0; kc < kChunks; ++kc)
@@ -739,10 +794,10 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
     } else if (warp == 1) {
         // ---- MMA issuer
         const u32 lbo_b = kC * 16;
-        const u32 desc_hi_a = umma_desc_hi(144), desc_hi_b = umma_desc_hi(128);
+        const u32 desc_hi_a = umma_desc_hi(Geo::kSbo), desc_hi_b = umma_desc_hi(128);
         const u32 a_k16_step = (2 * kLbo) >> 4, b_k16_step = (2 * lbo_b) >> 4;
-        const u32 x_lo = umma_desc_lo(smem_u32(s_x), kLbo) + (u32)(1 + kPairLine);
-        const u32 t_lo = umma_desc_lo(smem_u32(s_t), kLbo) + (u32)(1 + kPairLine);
+        const u32 x_lo = umma_desc_lo(smem_u32(s_x), kLbo) + (u32)Geo::kFirst;
+        const u32 t_lo = umma_desc_lo(smem_u32(s_t), kLbo) + (u32)Geo::kFirst;
         int j = 0, s = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             for (int layer = 0; layer < 2; ++layer) {
@@ -756,7 +811,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
                 const u32 a_lo_base = layer ? t_lo : x_lo;
                 const u32 d_base = tmem_base + (u32)(layer * kItemTiles * kC);
                 for (int tap = 0; tap < 9; ++tap) {
-                    const int shift = (tap / 3 - 1) * kPairLine + (tap % 3 - 1);
+                    const int shift = (tap / 3 - 1) * Geo::kLine + (tap % 3 - 1);
                     const u32 a_lo_tap = a_lo_base + (u32)shift;
                     for (int part = 0; part < kStagesPerTap; ++part, ++s) {
                         const int st = s % kStages2;
@@ -770,7 +825,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
                                 for (int kk = 0; kk < kStageK16; ++kk) {
                                     const int k16 = part * kStageK16 + kk;
                                     tc_mma_bf16(d_base + (u32)(tile * kC),
-                                                umma_desc_join(a_lo_tap + (u32)tile * kPairEntries + (u32)k16 * a_k16_step, desc_hi_a),
+                                                umma_desc_join(a_lo_tap + (u32)tile * Geo::kTileStep + (u32)k16 * a_k16_step, desc_hi_a),
                                                 umma_desc_join(b_lo + (u32)kk * b_k16_step, desc_hi_b), kIdescBf16,
                                                 (tap | k16) ? 1u : 0u);
                                 }
@@ -793,8 +848,8 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
     } else {
         // ---- epilogue warps 3..6
         const int quarter = warp & 3;
-        const int r = quarter * 32 + lane;   // accumulator lane = (line, board in pair, x)
-        const int grp = r >> 3, x = r & 7, y = grp >> 1;
+        const int r = quarter * 32 + lane;   // accumulator (TMEM) lane of this thread
+        constexpr int kCells = G * G;
         int j = 0;
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             // ---------- epilogue 1: acc1 -> +b1 -> ReLU -> bf16 -> bufT
@@ -802,25 +857,27 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
             tc_fence_after();
 #pragma unroll 1
             for (int tile = 0; tile < kItemTiles; ++tile) {
-                const u32 widx = (u32)(1 + kPairLine + tile * kPairEntries + grp * 9 + x);   // row inside the window
-                unsigned char* trow = s_t + (size_t)widx * 16;
+                const ResRow<G> row(it, tile, r);
+                unsigned char* trow = s_t + (size_t)row.widx * 16;
 #pragma unroll
                 for (int cc = 0; cc < kC / 32; ++cc) {
                     u32 v[32];
                     tc_ld32(tmem_base + ((u32)(quarter * 32) << 16) + (u32)(tile * kC + cc * 32), v);
                     tc_wait_ld();
+                    if (row.cell) {              // pad rows of T stay zero
 #pragma unroll
-                    for (int c4 = 0; c4 < 4; ++c4) {
-                        float f[8];
+                        for (int c4 = 0; c4 < 4; ++c4) {
+                            float f[8];
 #pragma unroll
-                        for (int jj = 0; jj < 8; ++jj)
-                            f[jj] = fmaxf(__uint_as_float(v[c4 * 8 + jj]) + args.bias1_c[cc * 32 + c4 * 8 + jj], 0.f);
-                        uint4 o;
-                        o.x = pack_bf16(f[0], f[1]);
-                        o.y = pack_bf16(f[2], f[3]);
-                        o.z = pack_bf16(f[4], f[5]);
-                        o.w = pack_bf16(f[6], f[7]);
-                        *reinterpret_cast<uint4*>(trow + (size_t)(cc * 4 + c4) * kLbo) = o;
+                            for (int jj = 0; jj < 8; ++jj)
+                                f[jj] = fmaxf(__uint_as_float(v[c4 * 8 + jj]) + args.bias1_c[cc * 32 + c4 * 8 + jj], 0.f);
+                            uint4 o;
+                            o.x = pack_bf16(f[0], f[1]);
+                            o.y = pack_bf16(f[2], f[3]);
+                            o.z = pack_bf16(f[4], f[5]);
+                            o.w = pack_bf16(f[6], f[7]);
+                            *reinterpret_cast<uint4*>(trow + (size_t)(cc * 4 + c4) * kLbo) = o;
+                        }
                     }
                 }
             }
@@ -834,9 +891,10 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
             bool waited = false;
 #pragma unroll 1
             for (int tile = 0; tile < kItemTiles; ++tile) {
-                const int b = 2 * (it * kPairItemPairs + tile) + (grp & 1);
-                const size_t m = pair_entry(b, y, x);
-                const bool valid = b < live;
+                const ResRow<G> row(it, tile, r);
+                const int b = row.b;
+                const size_t m = row.m;
+                const bool valid = row.cell && b < live;
                 uint4 res[kChunks];
                 if (valid) {
 #pragma unroll
@@ -883,7 +941,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc8(ResBlockArgs 
                         }
                     }
                 }
-                if (valid && args.vplane) args.vplane[(size_t)b * 64 + y * 8 + x] = fmaxf(vacc + args.vhead_b, 0.f);
+                if (valid && args.vplane) args.vplane[(size_t)b * kCells + row.y * G + row.x] = fmaxf(vacc + args.vhead_b, 0.f);
             }
             tc_fence_before();
             __syncwarp();
