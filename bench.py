@@ -364,12 +364,12 @@ def run_b200(args):
             "gpu_launches": int(tot_launches),
             "clocks": clock_info,
             "roofline": {
-                "kernel": "k_resblock_tc8 x3 + k_conv3x3_tc2 x1 per round (tcgen05 implicit-GEMM 3x3 convs: three fused "
+                "kernel": "k_resblock_tc<G> x3 + k_conv3x3_tc2 x1 per round (tcgen05 implicit-GEMM 3x3 convs: three fused "
                           "residual blocks and the policy conv; seven 128->128 convolutions in four launches)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops if peak_tflops else None,
                 "traffic": ncu_dram_traffic_per_launch() if wl["game"] == "othello" and args.trees == 4096 else None,
-                "traffic_unit": "DRAM bytes per k_resblock_tc8 launch (ncu --set full, "
+                "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch (ncu --set full, "
                                 "profiles/r1d_resblock_tc8_ncu_full_raw.csv; part of the 67 MB written stays in the 126 MB L2)",
                 # one fused residual block: the block input is read once (it is also the skip operand) and the
                 # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets; the
