@@ -372,10 +372,8 @@ def run_b200(args):
                 "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch (ncu --set full, "
                                 "profiles/r1d_resblock_tc8_ncu_full_raw.csv; part of the 67 MB written stays in the 126 MB L2)",
                 # one fused residual block: the block input is read once (it is also the skip operand) and the
-                # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets; the
-                # unfused g=7 path reads a padded (g+1)^2 window and writes g^2 cells per conv
-                "algorithmic_bytes_per_launch": (2 * args.trees * g * g * 256 + 2 * 9 * 128 * 128 * 2) if g == 8 else
-                (args.trees * (g + 1) ** 2 * 256 + args.trees * g * g * 256 + 9 * 128 * 128 * 2),
+                # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets
+                "algorithmic_bytes_per_launch": 2 * args.trees * g * g * 256 + 2 * 9 * 128 * 128 * 2,
                 "peak_source": peak_src, "launches": conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches if conv_launches else None,
                 "algorithmic_flop_per_launch": prof_leaf_evals * 7 * flop_per_leaf_conv / max(1, conv_launches),
