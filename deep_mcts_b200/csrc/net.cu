@@ -206,8 +206,9 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         return DM_ERR_INVALID;
     }
     int pe = prof_begin(net, 0, st);
-    netk::k_encode_conv1_table<<<(n + netk::kEncode3Boards - 1) / netk::kEncode3Boards, 256,
-                                 netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, first, second, player,
+    const int enc3_groups = (n + netk::kEncode3Boards - 1) / netk::kEncode3Boards;
+    const int enc3_blocks = std::min(enc3_groups, netk::kEncode3CtasPerSm * net->sm_count);
+    netk::k_encode_conv1_table<<<enc3_blocks, 256, netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, first, second, player,
                                                                          net->conv1_tab, net->conv1_base, C, net->a0,
                                                                          net->rows_total, net->pair_layout ? 1 : 0);
     prof_end(net, pe, st);
