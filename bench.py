@@ -70,10 +70,10 @@ def ncu_dram_traffic_per_launch():
 
 
 def tree_roofline(pd, tree_ms, peaks):
-    """HBM roofline of the two tree kernels from the run's own counters (SURVEY 8(d) byte model with
+    """HBM roofline of the tree kernel(s) from the run's own counters (SURVEY 8(d) byte model with
     f64 priors: child record visits 4 + value_sum 8 + prior 8 = 20 B, node header 16 B, path entry 4 B,
     state 17 B; expansion writes 26 B per child and reads 4*65 + 4 B of evaluator output; backup is a
-    12 B read + 12 B write per path node)."""
+    12 B read + 12 B write per path node).  A single pool runs both phases in one kernel (k_round)."""
     sims, depth, scanned = pd["simulations"], pd["depth_sum"], pd["children_scanned"]
     created, evals = pd["children_created"], pd["leaf_evals"]
     select_bytes = 16 * depth + 20 * scanned + 17 * sims + 4 * (depth + sims)
@@ -81,10 +81,13 @@ def tree_roofline(pd, tree_ms, peaks):
     peak = float(peaks.get("hbm_gbs", 6650.0)) if peaks else 6650.0
     out = {"bound": "hbm", "peak": peak, "unit": "GB/s",
            "note": "pointer-chasing kernels: dependent-load latency bound, far below the bandwidth roofline by construction"}
-    for name, nbytes in (("select", select_bytes), ("expand_backup", expand_bytes)):
+    for name, nbytes in (("select", select_bytes), ("expand_backup", expand_bytes),
+                         ("tree_round", select_bytes + expand_bytes)):
         ms = tree_ms.get(name, 0.0)
-        gbs = nbytes / (ms * 1e-3) / 1e9 if ms > 0 else None
-        out[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved": gbs, "frac": gbs / peak if gbs else None}
+        if ms <= 0:
+            continue
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        out[name] = {"algorithmic_bytes": nbytes, "ms": ms, "achieved": gbs, "frac": gbs / peak}
     return out
 
 
@@ -260,9 +263,9 @@ def run_b200(args):
             prof[k] = (prof.get(k, (0.0, 0))[0] + ms, prof.get(k, (0.0, 0))[1] + cnt)
         pdn.profile(False)
     p1 = engine.counters()
-    tree_ms = {"select": 0.0, "expand_backup": 0.0}
+    tree_ms = {}
     for name, a, b in (engine.tree_timers or []):
-        tree_ms[name] += a.elapsed_time(b)
+        tree_ms[name] = tree_ms.get(name, 0.0) + a.elapsed_time(b)
     engine.tree_timers = None
     pd = {k: p1[k] - p0[k] for k in p1}
     prof_leaf_evals = p1["leaf_evals"] - p0["leaf_evals"]
@@ -290,12 +293,12 @@ def run_b200(args):
     e2e_graph = None
     if args.graph:
         pool2.begin_step()
-        dn.search_round(pool2)
+        dn.run_search(pool2, 1)
         torch.cuda.synchronize()
         e2e_launches_before = lib.dm_launch_count()
         e2e_graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(e2e_graph):
-            dn.search_round(pool2)
+            dn.search_round(pool2, fused=True)
         e2e_round_launches = int(lib.dm_launch_count() - e2e_launches_before)
 
     def e2e_step():
@@ -305,11 +308,7 @@ def run_b200(args):
         _lib.call("dm_pool_set_root_state", pool2._h, 0, T, d_first.data_ptr(), d_second.data_ptr(),
                   d_player.data_ptr(), stream)
         pool2.begin_step()
-        if e2e_graph is not None:
-            for _ in range(sims + 1):
-                e2e_graph.replay()
-        else:
-            dn.run_search(pool2, sims)
+        dn.run_search(pool2, sims, round_graph=e2e_graph)
         _lib.call("dm_pool_root_visits", pool2._h, pool2._visits.data_ptr(), pool2._stats.data_ptr(), stream)
         h_visits.copy_(pool2._visits, non_blocking=True)
         h_stats.copy_(pool2._stats, non_blocking=True)

@@ -78,6 +78,7 @@ _SIGNATURES = {
     "dm_pool_leaf_buffers": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                      POINTER(c_void_p), POINTER(c_void_p)]),
     "dm_pool_expand_backup": (c_int, [_P, _P, c_int, _P, c_int, _P]),
+    "dm_pool_round": (c_int, [_P, _P, c_int, _P, c_int, c_int, _P]),
     "dm_pool_root_visits": (c_int, [_P, _P, _P, _P]),
     "dm_pool_root_children": (c_int, [_P, _P, _P, _P, _P]),
     "dm_pool_advance": (c_int, [_P, _P, _P]),

@@ -72,6 +72,13 @@ struct PoolView {
     u8* leaf_flags;
     int* leaf_tree;
     int* leaf_count;
+    // per-tree copy of the pending leaf (slot, state, flags): lets k_round expand it while other warps of the
+    // same launch already claim slots of the next batch
+    int* pend_slot;
+    u64* pend_first;
+    u64* pend_second;
+    u8* pend_player;
+    u8* pend_flags;
     // virtual-loss mode: up to DM_MAX_LEAVES pending paths per tree
     u32* vl_path;   // [n_trees][DM_MAX_LEAVES][DM_MAX_DEPTH]
     int* vl_len;    // [n_trees][DM_MAX_LEAVES]
@@ -803,13 +810,8 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
 constexpr int kLevelBudget = 32;
 
 template <bool kSelfPlay>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
-    __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= P.n_trees) return;
+__device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, u32* path) {
     const size_t base = (size_t)t * P.cap;
-    u32* path = s_path[warp];
     unsigned long long scanned = 0, depth = 0, terminal = 0, done = 0;
     if (kSelfPlay) {
         if (P.sims_left[t] <= 0) {
@@ -878,6 +880,11 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
             P.leaf_player[slot] = (u8)s.player;
             P.leaf_flags[slot] = leaf_flag;
             P.leaf_tree[slot] = t;
+            P.pend_slot[t] = slot;
+            P.pend_first[t] = s.first;
+            P.pend_second[t] = s.second;
+            P.pend_player[t] = (u8)s.player;
+            P.pend_flags[t] = leaf_flag;
         }
         emitted = true;
         break;
@@ -894,35 +901,34 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
     }
 }
 
-// expand_node + rollout mix + backpropagate for the leaves handed out by k_select
-template <typename PriorT>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    k_expand_backup(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
-    __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+template <bool kSelfPlay>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
+    __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int slot = blockIdx.x * kWarpsPerBlock + warp;
-    if (slot >= *P.leaf_count) return;
-    int t = P.leaf_tree[slot];
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    select_tree<kSelfPlay>(P, t, lane, s_path[warp]);
+}
+
+// expand_node + rollout mix + backpropagate for one pending leaf (state s, evaluator output in slot `slot`)
+template <typename PriorT>
+__device__ __forceinline__ void expand_backup_tree(const PoolView& P, int t, int slot, int lane, const GState& s,
+                                                   u8 leaf_flag, u8* order, const PriorT* priors, int stride,
+                                                   const PriorT* values) {
     const size_t base = (size_t)t * P.cap;
-    int len = P.path_len[t];
-    if (len <= 0) return;
+    const int len = P.path_len[t];
     const u32* path = P.path + (size_t)t * DM_MAX_DEPTH;
-    GState s;
-    s.first = P.leaf_first[slot];
-    s.second = P.leaf_second[slot];
-    s.player = P.leaf_player[slot];
-    u8 leaf_flag = P.leaf_flags[slot];
     double ev;
     const PriorT* pr = priors + (size_t)slot * stride;
     bool ok;
-    if (sizeof(PriorT) == 8) ok = expand(P, t, lane, path[len - 1], s, s_order[warp], DM_EVAL_EXTERNAL, nullptr,
-                                         (const double*)pr, ev);
-    else ok = expand(P, t, lane, path[len - 1], s, s_order[warp], DM_EVAL_EXTERNAL, (const float*)pr, nullptr, ev);
+    if (sizeof(PriorT) == 8) ok = expand(P, t, lane, path[len - 1], s, order, DM_EVAL_EXTERNAL, nullptr, (const double*)pr, ev);
+    else ok = expand(P, t, lane, path[len - 1], s, order, DM_EVAL_EXTERNAL, (const float*)pr, nullptr, ev);
     if (!ok) {
         if (lane == 0) {
             P.sims_left[t] = 0;
             P.path_len[t] = 0;
         }
+        __syncwarp();
         return;
     }
     unsigned long long plies = 0;
@@ -954,6 +960,46 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
         count(P, kCntLeafEvals, 1);
         count(P, kCntRolloutPlies, plies);
     }
+    __syncwarp();
+}
+
+template <typename PriorT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+    k_expand_backup(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
+    __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int slot = blockIdx.x * kWarpsPerBlock + warp;
+    if (slot >= *P.leaf_count) return;
+    int t = P.leaf_tree[slot];
+    if (P.path_len[t] <= 0) return;
+    GState s;
+    s.first = P.leaf_first[slot];
+    s.second = P.leaf_second[slot];
+    s.player = P.leaf_player[slot];
+    expand_backup_tree<PriorT>(P, t, slot, lane, s, P.leaf_flags[slot], s_order[warp], priors, stride, values);
+}
+
+// One launch per search round: expand + back up the tree's pending leaf with the evaluator's output,
+// then go straight on to the next selection (mcts.py:119-138: the body of the simulation loop).
+// The pending leaf is read from the per-tree copy, because other warps of this launch are already
+// claiming slots of the next leaf batch; the evaluator outputs (indexed by the OLD slot) are not
+// touched by this kernel.  Saves a kernel boundary per round and finds the path's nodes cache-hot.
+template <bool kSelfPlay, typename PriorT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
+    k_round(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
+    __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
+    __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    if (P.path_len[t] > 0) {
+        GState s;
+        s.first = P.pend_first[t];
+        s.second = P.pend_second[t];
+        s.player = P.pend_player[t];
+        expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
+    }
+    select_tree<kSelfPlay>(P, t, lane, s_path[warp]);
 }
 
 // ---------------------------------------------------------------- virtual-loss mode
@@ -1292,6 +1338,9 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
         (rc = pool_alloc(p, &v.path_len, T)) || (rc = pool_alloc(p, &v.leaf_first, T * DM_MAX_LEAVES)) ||
         (rc = pool_alloc(p, &v.leaf_second, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.leaf_player, T * DM_MAX_LEAVES)) ||
         (rc = pool_alloc(p, &v.leaf_flags, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.leaf_tree, T * DM_MAX_LEAVES)) ||
+        (rc = pool_alloc(p, &v.pend_slot, T)) || (rc = pool_alloc(p, &v.pend_first, T)) ||
+        (rc = pool_alloc(p, &v.pend_second, T)) || (rc = pool_alloc(p, &v.pend_player, T)) ||
+        (rc = pool_alloc(p, &v.pend_flags, T)) ||
         (rc = pool_alloc(p, &v.vl_len, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.vl_slot, T * DM_MAX_LEAVES)) ||
         (rc = pool_alloc(p, &v.vl_count, T)) || (rc = pool_alloc(p, &v.armed, 1)) ||
         (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)))
@@ -1484,6 +1533,32 @@ extern "C" int dm_pool_expand_backup(dm_pool* p, const void* priors, int stride,
     else
         k_expand_backup<float><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
             p->v, (const float*)priors, stride, (const float*)values);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
+extern "C" int dm_pool_round(dm_pool* p, const void* priors, int stride, const void* values, int is_f64, int selfplay,
+                             void* stream) {
+    DM_CHECK_ARG(p && priors && values, "dm_pool_round: null argument");
+    DM_CHECK_ARG(stride >= p->v.cfg.num_actions, "dm_pool_round: prior_stride < num_actions");
+    if (!p->configured || p->v.eval_kind != DM_EVAL_EXTERNAL || p->v.leaves_per_round != 1) {
+        dm_set_error("dm_pool_round: needs eval_kind EXTERNAL and leaves_per_round 1");
+        return DM_ERR_STATE;
+    }
+    if (selfplay && !p->v.selfplay) {
+        dm_set_error("dm_pool_round: self-play recording is not enabled on this pool");
+        return DM_ERR_STATE;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    DM_CUDA(cudaMemsetAsync(p->v.leaf_count, 0, sizeof(int), st));
+    const int blocks = tree_blocks(p->v.n_trees), threads = kWarpsPerBlock * 32;
+    if (is_f64) {
+        if (selfplay) k_round<true, double><<<blocks, threads, 0, st>>>(p->v, (const double*)priors, stride, (const double*)values);
+        else k_round<false, double><<<blocks, threads, 0, st>>>(p->v, (const double*)priors, stride, (const double*)values);
+    } else {
+        if (selfplay) k_round<true, float><<<blocks, threads, 0, st>>>(p->v, (const float*)priors, stride, (const float*)values);
+        else k_round<false, float><<<blocks, threads, 0, st>>>(p->v, (const float*)priors, stride, (const float*)values);
+    }
     DM_LAUNCH_CHECK();
     return DM_OK;
 }

@@ -38,8 +38,11 @@ class DeviceNet:
         self._h = handle
         self._loaded = False
         A = _lib.DM_MAX_ACTIONS
+        # outputs of the search path: a fused round leaves its last batch pending here until the next round
         self._value = torch.zeros(self.max_batch, dtype=torch.float32, device=self.device)
         self._probs = torch.zeros((self.max_batch, A), dtype=torch.float32, device=self.device)
+        # outputs of the host-facing calls (evaluate / forward), kept apart so they never clobber a pending batch
+        self._host_value = self._host_probs = None
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -84,6 +87,12 @@ class DeviceNet:
                       self._probs.data_ptr(), current_stream())
         return self._value, self._probs
 
+    def _host_outputs(self) -> Tuple[torch.Tensor, torch.Tensor]:
+        if self._host_value is None:
+            self._host_value = torch.zeros_like(self._value)
+            self._host_probs = torch.zeros_like(self._probs)
+        return self._host_value, self._host_probs
+
     def _upload(self, player, first, second):
         f = torch.from_numpy(np.asarray(first, dtype=np.uint64).view(np.int64)).to(self.device)
         s = torch.from_numpy(np.asarray(second, dtype=np.uint64).view(np.int64)).to(self.device)
@@ -94,7 +103,11 @@ class DeviceNet:
         """Host arrays in, host arrays out: (value[n], probs[n, num_actions])."""
         f, s, p = self._upload(player, first, second)
         n = f.numel()
-        value, probs = self.evaluate_device(f, s, p, n, None, precision)
+        self._check(n)
+        value, probs = self._host_outputs()
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_evaluate", self._h, PRECISIONS[precision or self.precision], n, 0, f.data_ptr(),
+                      s.data_ptr(), p.data_ptr(), value.data_ptr(), probs.data_ptr(), current_stream())
         return value[:n].cpu().numpy(), probs[:n, : self.manager.num_actions].cpu().numpy()
 
     def forward(self, player, first, second, precision: Optional[str] = None) -> Tuple[np.ndarray, np.ndarray]:
@@ -103,10 +116,11 @@ class DeviceNet:
         n = f.numel()
         self._check(n)
         prec = PRECISIONS[precision or self.precision]
+        value, probs = self._host_outputs()
         with torch.cuda.device(self.device):
             _lib.call("dm_net_forward", self._h, prec, n, f.data_ptr(), s.data_ptr(), p.data_ptr(),
-                      self._value.data_ptr(), self._probs.data_ptr(), current_stream())
-        return self._value[:n].cpu().numpy(), self._probs[:n, : self.manager.num_actions].cpu().numpy()
+                      value.data_ptr(), probs.data_ptr(), current_stream())
+        return value[:n].cpu().numpy(), probs[:n, : self.manager.num_actions].cpu().numpy()
 
     def rollout_greedy(self, player, first, second, precision: Optional[str] = None) -> np.ndarray:
         """Outcome of playing argmax of the masked policy from every state
@@ -141,10 +155,26 @@ class DeviceNet:
         return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(("encode", "trunk_conv", "heads"))}
 
     # --------------------------------------------------------------------------- search
-    def search_round(self, pool, selfplay: bool = False, timers: Optional[list] = None) -> None:
-        """One select -> evaluate -> expand/backup round for every tree of the pool (no host sync).
-        ``timers`` (a list) receives CUDA-event pairs around the two tree kernels:
-        ("select", start, stop), ("expand_backup", start, stop)."""
+    def search_round(self, pool, selfplay: bool = False, timers: Optional[list] = None, fused: bool = False) -> None:
+        """One search round for every tree of the pool (no host sync).
+
+        ``fused = False``: select -> evaluate -> expand/backup (three steps, the tree is complete at
+        the end).  ``fused = True``: one tree kernel (expand/backup of the leaves evaluated in the
+        previous round, then the next selection) -> evaluate; the last batch stays pending and is
+        consumed by the next fused round (or by ``evaluate_pending`` / an unfused round, which
+        simply selects again).
+        ``timers`` (a list) receives CUDA-event pairs around the tree kernels:
+        ("select", start, stop) and ("expand_backup", start, stop), or ("tree_round", start, stop)."""
+        if fused:
+            if timers is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ev[0].record()
+            pool.round(self._probs, self._value, selfplay)
+            if timers is not None:
+                ev[1].record()
+                timers.append(("tree_round", ev[0], ev[1]))
+            self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity, pool.leaf_count)
+            return
         if timers is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             ev[0].record()
@@ -170,12 +200,22 @@ class DeviceNet:
                                             pool.leaf_count)
         pool.expand_backup(probs, value)
 
-    def run_search(self, pool, sims: int) -> None:
-        """All armed simulations of one MCTS.step.  Exact mode: at most sims + 1 rounds (root
-        expansion), no host synchronisation.  Virtual-loss mode: rounds until no tree hands out a leaf."""
+    def run_search(self, pool, sims: int, round_graph=None) -> None:
+        """All armed simulations of one MCTS.step.  Exact mode: sims + 1 selections (root expansion),
+        no host synchronisation; ``round_graph`` is an optional captured CUDA graph of
+        ``search_round(pool, fused=True)`` to replay instead of launching the round.
+        Virtual-loss mode: rounds until no tree hands out a leaf."""
         if pool.leaves_per_round == 1:
-            for _ in range(int(sims) + 1):
-                self.search_round(pool)
+            # select + evaluate, then `sims` fused rounds (expand/backup -> select -> evaluate), then the
+            # last batch's expand/backup
+            pool.select()
+            self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity, pool.leaf_count)
+            for _ in range(int(sims)):
+                if round_graph is not None:
+                    round_graph.replay()
+                else:
+                    self.search_round(pool, fused=True)
+            pool.expand_backup(self._probs, self._value)
             return
         for _ in range(int(sims) + 2):
             self.search_round(pool)

@@ -173,6 +173,16 @@ class TreePool:
             _lib.call("dm_pool_expand_backup", self._h, priors.data_ptr(), int(priors.shape[1]),
                       values.data_ptr(), is_f64, self._stream())
 
+    def round(self, priors: torch.Tensor, values: torch.Tensor, selfplay: bool = False) -> None:
+        """Expand + back up every pending leaf from the evaluator output of the previous batch, then
+        select the next leaf of every tree, in one launch (``dm_pool_round``)."""
+        assert priors.is_cuda and values.is_cuda and priors.dtype == values.dtype
+        assert priors.is_contiguous() and values.is_contiguous()
+        assert priors.dtype in (torch.float32, torch.float64)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_round", self._h, priors.data_ptr(), int(priors.shape[1]), values.data_ptr(),
+                      1 if priors.dtype == torch.float64 else 0, 1 if selfplay else 0, self._stream())
+
     def step_external(self, evaluate: Callable[[np.ndarray, np.ndarray, np.ndarray], Tuple[np.ndarray, np.ndarray]],
                       max_rounds: Optional[int] = None) -> None:
         """Run the armed simulations with a HOST evaluator: ``evaluate(player, first, second)``

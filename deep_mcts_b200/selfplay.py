@@ -87,7 +87,9 @@ class BatchedSelfPlay:
                 dn.load_state_dict(sd)
 
     def run_rounds(self, rounds: int) -> None:
-        """``rounds`` x (select one leaf per tree -> network batch -> expand + backup) for every pool."""
+        """``rounds`` search rounds for every pool.  A single pool runs fused rounds (expand + backup of the
+        previous batch and the next selection in one tree kernel, then the network batch), so the
+        last batch stays pending between calls; several pools run select -> network -> expand/backup."""
         if self.n_pools == 1:
             dn, pool = self.device_nets[0], self.pools[0]
             if self.use_graph:
@@ -98,7 +100,7 @@ class BatchedSelfPlay:
                 self.graph_replays += int(rounds)
                 return
             for _ in range(int(rounds)):
-                dn.search_round(pool, selfplay=True, timers=self.tree_timers)
+                dn.search_round(pool, selfplay=True, timers=self.tree_timers, fused=True)
             return
         if self.use_graph:
             if self._graph is None:
@@ -126,16 +128,17 @@ class BatchedSelfPlay:
             current.wait_stream(st)
 
     def _capture_round(self) -> None:
-        """Capture one select -> network -> expand/backup round (kernel launches + 1 memset) into a
-        CUDA graph; the round has no host-visible state, so replaying it is identical to launching it."""
+        """Capture one fused round (memset + tree kernel: expand/backup of the previous batch and the next
+        selection, then the network kernels) into a CUDA graph; the round has no host-visible state, so
+        replaying it is identical to launching it."""
         dn, pool = self.device_nets[0], self.pools[0]
-        dn.search_round(pool, selfplay=True)        # warm every kernel outside the capture
+        dn.search_round(pool, selfplay=True, fused=True)        # warm every kernel outside the capture
         torch.cuda.synchronize()
         lib = _lib.load()
         before = lib.dm_launch_count()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            dn.search_round(pool, selfplay=True)
+            dn.search_round(pool, selfplay=True, fused=True)
         self._graph_launches = int(lib.dm_launch_count() - before)
         self._graph = graph
 

@@ -176,6 +176,14 @@ int dm_pool_leaf_buffers(dm_pool* pool, uint64_t** first_dev, uint64_t** second_
  * and priors_dev[slot][prior_stride] per pending leaf, as float (is_f64 = 0) or double. */
 int dm_pool_expand_backup(dm_pool* pool, const void* priors_dev, int prior_stride, const void* values_dev,
                           int is_f64, void* stream);
+/* phase 2 of the previous round and phase 1 of the next in ONE launch (the body of the simulation
+ * loop, mcts.py:119-138): every tree with a pending leaf expands it and backs it up from
+ * values_dev / priors_dev (indexed by the slot the leaf was handed out in), then selects its next
+ * leaf into the leaf buffers.  selfplay != 0 gives the selection dm_selfplay_select's move-making
+ * (needs dm_selfplay_enable).  Exact mode only (leaves_per_round 1).  The evaluator outputs of the
+ * previous batch must stay untouched until this call has run. */
+int dm_pool_round(dm_pool* pool, const void* priors_dev, int prior_stride, const void* values_dev, int is_f64,
+                  int selfplay, void* stream);
 /* result of MCTS.step (mcts.py:139-148): visits_dev[n_trees][DM_MAX_ACTIONS] root child visit
  * counts by action, stats_dev[n_trees][2] = (with expansion, without expansion) */
 int dm_pool_root_visits(dm_pool* pool, uint32_t* visits_dev, uint32_t* stats_dev, void* stream);
