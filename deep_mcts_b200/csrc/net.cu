@@ -230,18 +230,21 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     if (net->fused_blocks) {
         // one fused launch per residual block: conv1 -> T (shared memory) -> conv2 + skip
         netk::ResBlockArgs ra;
-        memset(&ra, 0, sizeof(ra));
-        ra.x = net->a0;
-        ra.out = net->a0;
-        ra.rows_total = net->rows_total;
-        ra.n_boards = n;
-        ra.count_dev = count_dev;
-        for (int i = 0; i < R; ++i) {
-            ra.w1 = net->trunk_w16[2 * i];
-            ra.w2 = net->trunk_w16[2 * i + 1];
-            memcpy(ra.bias1_c, net->h_trunk_b[2 * i].data(), sizeof(ra.bias1_c));
-            memcpy(ra.bias2_c, net->h_trunk_b[2 * i + 1].data(), sizeof(ra.bias2_c));
-            if (i == R - 1) {
+        for (int i0 = 0; i0 < R; i0 += netk::kMaxFusedBlocks) {
+            memset(&ra, 0, sizeof(ra));
+            ra.x = net->a0;
+            ra.rows_total = net->rows_total;
+            ra.n_boards = n;
+            ra.count_dev = count_dev;
+            ra.n_blocks = std::min(netk::kMaxFusedBlocks, R - i0);
+            for (int k = 0; k < ra.n_blocks; ++k) {
+                const int i = i0 + k;
+                ra.w1[k] = net->trunk_w16[2 * i];
+                ra.w2[k] = net->trunk_w16[2 * i + 1];
+                memcpy(ra.bias1_c[k], net->h_trunk_b[2 * i].data(), sizeof(ra.bias1_c[k]));
+                memcpy(ra.bias2_c[k], net->h_trunk_b[2 * i + 1].data(), sizeof(ra.bias2_c[k]));
+            }
+            if (i0 + ra.n_blocks == R) {
                 ra.vplane = net->vplane;
                 ra.vhead_b = net->vconv_b;
                 memcpy(ra.vw_c, net->h_vconv_w.data(), sizeof(ra.vw_c));

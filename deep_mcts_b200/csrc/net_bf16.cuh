@@ -687,18 +687,23 @@ struct ResRow {
     }
 };
 
+// Up to kMaxFusedBlocks consecutive residual blocks run in ONE launch: a CTA keeps the same items in
+// every block and a 3x3 conv never crosses a board, so block b+1 of an item depends only on what this
+// CTA itself wrote for that item in block b -- no grid-wide synchronisation, just an in-CTA "output
+// of item j is visible" counter between the epilogue warps and the X producer.
+constexpr int kMaxFusedBlocks = 3;
 struct ResBlockArgs {
-    const __nv_bfloat16* x;      // block input (also the residual)
-    __nv_bfloat16* out;          // block output, same layout (may alias x)
-    const __nv_bfloat16* w1;     // [9][16][128][8]
-    const __nv_bfloat16* w2;
+    __nv_bfloat16* x;            // activations, updated in place block after block (input = residual of block 0)
+    const __nv_bfloat16* w1[kMaxFusedBlocks];     // [9][16][128][8] per layer
+    const __nv_bfloat16* w2[kMaxFusedBlocks];
     float vhead_b;
-    float* vplane;               // non-null on the last block: value-head 1x1 conv of the output
+    float* vplane;               // non-null: value-head 1x1 conv of the last block's output
     size_t rows_total;
     int n_boards;
+    int n_blocks;
     const int* count_dev;
-    float bias1_c[128];
-    float bias2_c[128];
+    float bias1_c[kMaxFusedBlocks][128];
+    float bias2_c[kMaxFusedBlocks][128];
     float vw_c[128];
 };
 
@@ -728,9 +733,12 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
     const u32 bar_acc1 = smem_u32(&s_bar[2 * kStages2 + 2]), bar_tfull = smem_u32(&s_bar[2 * kStages2 + 3]);
     const u32 bar_acc2 = smem_u32(&s_bar[2 * kStages2 + 4]), bar_acc2empty = smem_u32(&s_bar[2 * kStages2 + 5]);
     u32* s_tmem = (u32*)(s_bar + 2 * kStages2 + 8);
+    volatile u32* s_done = s_tmem + 1;   // epilogue-warp arrivals: 4 per item whose block output is in global memory
+    const int n_local = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;   // items of this CTA
 
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) *s_done = 0;
     // bufT pads must read as zero for conv2: clear it once, the epilogue only ever writes real cells
     for (u32 i = threadIdx.x; i < kBufBytes / 16; i += blockDim.x)
         reinterpret_cast<uint4*>(s_t)[i] = make_uint4(0, 0, 0, 0);
@@ -760,11 +768,12 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
     const u32 tmem_base = *s_tmem;
 
     if (warp == 0) {
-        // ---- weight producer: layer 1 then layer 2 of every item
+        // ---- weight producer: layer 1 then layer 2 of every item, block after block
         int s = 0;
+        for (int blk = 0; blk < args.n_blocks; ++blk)
         for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
             for (int layer = 0; layer < 2; ++layer) {
-                const unsigned char* w = reinterpret_cast<const unsigned char*>(layer ? args.w2 : args.w1);
+                const unsigned char* w = reinterpret_cast<const unsigned char*>(layer ? args.w2[blk] : args.w1[blk]);
                 for (int part = 0; part < 9 * kStagesPerTap; ++part, ++s) {
                     const int st = s % kStages2;
                     if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
@@ -780,8 +789,21 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
     } else if (warp == 2) {
         // ---- X producer (single buffer: refilled as soon as conv1 of the previous item has retired)
         int j = 0;
+        for (int blk = 0; blk < args.n_blocks; ++blk)
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             if (j >= 1) mbar_wait(bar_xfree, (j - 1) & 1);
+            if (blk > 0) {
+                // this item's output of the previous block (written by this CTA's epilogue warps) must be in
+                // global memory before the bulk copy reads it back
+                const u32 need = 4u * (u32)(j - n_local + 1);
+                u32 spins = 0;
+                while (*s_done < need) {
+                    __nanosleep(64);
+                    if (++spins > (1u << 24)) __trap();
+                }
+                __threadfence();
+                asm volatile("fence.proxy.async;" ::: "memory");
+            }
             const size_t row0 = Geo::window_row0(it);
             if (elect_one()) {
                 mbar_expect_tx(bar_xfull, kLbo * kChunks);
@@ -799,6 +821,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
         const u32 x_lo = umma_desc_lo(smem_u32(s_x), kLbo) + (u32)Geo::kFirst;
         const u32 t_lo = umma_desc_lo(smem_u32(s_t), kLbo) + (u32)Geo::kFirst;
         int j = 0, s = 0;
+        for (int blk = 0; blk < args.n_blocks; ++blk)
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
             for (int layer = 0; layer < 2; ++layer) {
                 if (layer == 0) {
@@ -851,7 +874,12 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
         const int r = quarter * 32 + lane;   // accumulator (TMEM) lane of this thread
         constexpr int kCells = G * G;
         int j = 0;
+#pragma unroll 1
+        for (int blk = 0; blk < args.n_blocks; ++blk)
         for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++j) {
+            const float* bias1 = args.bias1_c[blk];
+            const float* bias2 = args.bias2_c[blk];
+            const bool emit_v = args.vplane != nullptr && blk == args.n_blocks - 1;
             // ---------- epilogue 1: acc1 -> +b1 -> ReLU -> bf16 -> bufT
             mbar_wait(bar_acc1, j & 1);
             tc_fence_after();
@@ -870,7 +898,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
                             float f[8];
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj)
-                                f[jj] = fmaxf(__uint_as_float(v[c4 * 8 + jj]) + args.bias1_c[cc * 32 + c4 * 8 + jj], 0.f);
+                                f[jj] = fmaxf(__uint_as_float(v[c4 * 8 + jj]) + bias1[cc * 32 + c4 * 8 + jj], 0.f);
                             uint4 o;
                             o.x = pack_bf16(f[0], f[1]);
                             o.y = pack_bf16(f[2], f[3]);
@@ -920,15 +948,15 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
                             float f[8];
 #pragma unroll
                             for (int jj = 0; jj < 4; ++jj) {
-                                f[2 * jj] = __uint_as_float(v[c4 * 8 + 2 * jj]) + args.bias2_c[cc * 32 + c4 * 8 + 2 * jj] +
+                                f[2 * jj] = __uint_as_float(v[c4 * 8 + 2 * jj]) + bias2[cc * 32 + c4 * 8 + 2 * jj] +
                                             __uint_as_float(rw[jj] << 16);
                                 f[2 * jj + 1] = __uint_as_float(v[c4 * 8 + 2 * jj + 1]) +
-                                                args.bias2_c[cc * 32 + c4 * 8 + 2 * jj + 1] +
+                                                bias2[cc * 32 + c4 * 8 + 2 * jj + 1] +
                                                 __uint_as_float(rw[jj] & 0xffff0000u);
                             }
 #pragma unroll
                             for (int jj = 0; jj < 8; ++jj) f[jj] = fmaxf(f[jj], 0.f);
-                            if (args.vplane) {
+                            if (emit_v) {
 #pragma unroll
                                 for (int jj = 0; jj < 8; ++jj) vacc = fmaf(f[jj], args.vw_c[cc * 32 + c4 * 8 + jj], vacc);
                             }
@@ -937,15 +965,21 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
                             o.y = pack_bf16(f[2], f[3]);
                             o.z = pack_bf16(f[4], f[5]);
                             o.w = pack_bf16(f[6], f[7]);
-                            *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
+                            *reinterpret_cast<uint4*>(args.x + ((size_t)(cc * 4 + c4) * args.rows_total + m) * 8) = o;
                         }
                     }
                 }
-                if (valid && args.vplane) args.vplane[(size_t)b * kCells + row.y * G + row.x] = fmaxf(vacc + args.vhead_b, 0.f);
+                if (valid && emit_v) args.vplane[(size_t)b * kCells + row.y * G + row.x] = fmaxf(vacc + args.vhead_b, 0.f);
             }
             tc_fence_before();
+            // the item's block output is written: make it visible to the bulk copies of the next block
+            __threadfence();
+            asm volatile("fence.proxy.async;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acc2empty);
+            if (lane == 0) {
+                mbar_arrive(bar_acc2empty);
+                atomicAdd((u32*)s_done, 1u);
+            }
         }
     }
     tc_fence_before();
