@@ -778,9 +778,16 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
                     const int st = s % kStages2;
                     if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
                     if (elect_one()) {
+#ifdef DM_EXP_NOWEIGHTS
+                        if (s >= kStages2) {   // timing experiment: signal "full" without streaming the weights again
+                            mbar_arrive(bar_bfull + 8 * st);
+                        } else
+#endif
+                        {
                         mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
                         bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes), w + (size_t)part * kStage2Bytes, kStage2Bytes,
                                  bar_bfull + 8 * st);
+                        }
                     }
                     __syncwarp();
                 }
