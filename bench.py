@@ -52,13 +52,16 @@ def parse_args():
 
 
 def ncu_dram_traffic_per_launch():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the fused residual-block kernel from the
-    committed `ncu --set full` capture (profiles/), averaged over the captured launches; None if absent."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the fused residual-block kernel (three blocks per
+    launch) from the committed `ncu --set full` capture (profiles/), averaged over the captured launches;
+    None if absent."""
     import csv
-    path = ROOT / "profiles" / "r1d_resblock_tc8_ncu_full_raw.csv"
+    path = ROOT / "profiles" / "r1e_round_kernels_ncu_full_raw.csv"
     try:
         rows = list(csv.reader(open(path)))
-        hdr, units, data = rows[0], rows[1], rows[2:]
+        hdr, units = rows[0], rows[1]
+        name = hdr.index("Kernel Name")
+        data = [r for r in rows[2:] if "k_resblock_tc" in r[name]]
         total = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = hdr.index(key)
@@ -363,16 +366,18 @@ def run_b200(args):
             "gpu_launches": int(tot_launches),
             "clocks": clock_info,
             "roofline": {
-                "kernel": "k_resblock_tc<G> x3 + k_conv3x3_tc2 x1 per round (tcgen05 implicit-GEMM 3x3 convs: three fused "
-                          "residual blocks and the policy conv; seven 128->128 convolutions in four launches)",
+                "kernel": "k_resblock_tc<G> x1 + k_conv3x3_tc2 x1 per round (tcgen05 implicit-GEMM 3x3 convs: the three fused "
+                          "residual blocks in one launch and the policy conv; seven 128->128 convolutions in two launches)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops if peak_tflops else None,
                 "traffic": ncu_dram_traffic_per_launch() if wl["game"] == "othello" and args.trees == 4096 else None,
-                "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch (ncu --set full, "
-                                "profiles/r1d_resblock_tc8_ncu_full_raw.csv; part of the 67 MB written stays in the 126 MB L2)",
-                # one fused residual block: the block input is read once (it is also the skip operand) and the
-                # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets
-                "algorithmic_bytes_per_launch": 2 * args.trees * g * g * 256 + 2 * 9 * 128 * 128 * 2,
+                "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch = three residual blocks (ncu --set full, "
+                                "profiles/r1e_round_kernels_ncu_full_raw.csv; the blocks' intermediate activations "
+                                "are re-read from the 126 MB L2)",
+                # per fused residual block: the block input is read once (it is also the skip operand) and the
+                # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets; a launch
+                # runs the trunk's three blocks
+                "algorithmic_bytes_per_launch": 3 * (2 * args.trees * g * g * 256 + 2 * 9 * 128 * 128 * 2),
                 "peak_source": peak_src, "launches": conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches if conv_launches else None,
                 "algorithmic_flop_per_launch": prof_leaf_evals * 7 * flop_per_leaf_conv / max(1, conv_launches),
