@@ -1161,11 +1161,30 @@ __global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg
     for (int p = lane; p < P0; p += 32) s_vp[warp][p] = vplane[(size_t)gb * P0 + p];
     __syncwarp();
     float v = 0.f;
-    for (int j = lane; j < hp.H; j += 32) {
-        // vfc1_t is the transposed weight [pos][H]: lanes read consecutive hidden units
-        float acc = hp.vfc1_b[j];
-        for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], s_w1[p * hp.H + j], acc);
-        v = fmaf(fmaxf(acc, 0.f), hp.vfc2_w[j], v);
+    if ((hp.H & 127) == 0) {
+        // vfc1_t is the transposed weight [pos][H]: a lane owns four consecutive hidden units, so one
+        // 16-byte shared-memory read per position feeds four FMAs (same summation order as below)
+        for (int j0 = lane * 4; j0 < hp.H; j0 += 128) {
+            float a0 = hp.vfc1_b[j0], a1 = hp.vfc1_b[j0 + 1], a2 = hp.vfc1_b[j0 + 2], a3 = hp.vfc1_b[j0 + 3];
+            for (int p = 0; p < P0; ++p) {
+                const float x = s_vp[warp][p];
+                const float4 w = *reinterpret_cast<const float4*>(s_w1 + p * hp.H + j0);
+                a0 = fmaf(x, w.x, a0);
+                a1 = fmaf(x, w.y, a1);
+                a2 = fmaf(x, w.z, a2);
+                a3 = fmaf(x, w.w, a3);
+            }
+            v = fmaf(fmaxf(a0, 0.f), hp.vfc2_w[j0], v);
+            v = fmaf(fmaxf(a1, 0.f), hp.vfc2_w[j0 + 1], v);
+            v = fmaf(fmaxf(a2, 0.f), hp.vfc2_w[j0 + 2], v);
+            v = fmaf(fmaxf(a3, 0.f), hp.vfc2_w[j0 + 3], v);
+        }
+    } else {
+        for (int j = lane; j < hp.H; j += 32) {
+            float acc = hp.vfc1_b[j];
+            for (int p = 0; p < P0; ++p) acc = fmaf(s_vp[warp][p], s_w1[p * hp.H + j], acc);
+            v = fmaf(fmaxf(acc, 0.f), hp.vfc2_w[j], v);
+        }
     }
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(DM_FULL_MASK, v, off);
