@@ -6,8 +6,9 @@ Same semantics as reference deep_mcts/tournament.py:55-108 with ``MCTSAgent`` pl
 from it with probability epsilon -- but every game of the match advances in lock-step on the
 device: one ``BatchedMCTS`` per agent with one tree per game.
 """
+import itertools
 from dataclasses import dataclass
-from typing import Callable, Optional, Sequence, Tuple
+from typing import Callable, List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -86,3 +87,17 @@ def compare_agents_batched(specs: Tuple[AgentSpec, AgentSpec], num_games: int, m
     draws = ((as_first == 0.5).sum() / half, (as_second == 0.5).sum() / half)
     losses = ((as_first == 1.0).sum() / half, (as_second == 0.0).sum() / half)
     return (tuple(float(x) for x in wins), tuple(float(x) for x in draws), tuple(float(x) for x in losses))
+
+
+def tournament_batched(specs: Sequence[AgentSpec], num_games: int, manager: BoardManager,
+                       seed: int = 0) -> List[List[AgentComparison]]:
+    """Round robin incl. self-matches, result[i][j] = comparison of agent i against agent j and the
+    mirrored entry with wins and losses swapped (reference tournament.py:84-94)."""
+    n = len(specs)
+    zero = ((0.0, 0.0), (0.0, 0.0), (0.0, 0.0))
+    results = [[zero for _ in range(n)] for _ in range(n)]
+    for k, ((i, a), (j, b)) in enumerate(itertools.combinations_with_replacement(enumerate(specs), 2)):
+        result = compare_agents_batched((a, b), num_games, manager, seed + 7919 * k)
+        results[i][j] = result
+        results[j][i] = (result[2], result[1], result[0])
+    return results
