@@ -249,3 +249,27 @@ def test_config1_tictactoe_net_search_exact_over_100_games():
                 live[t] = False
         batch.advance(actions)
     assert moves > 500 and batch.pool.counters()["capacity_errors"] == 0
+
+
+@pytest.mark.parametrize("name,g", [("othello", 8), ("hex", 7)])
+def test_full_batch_is_bitwise_equal_to_small_batches(name, g):
+    """BASELINE-size batch (4096 leaves: every persistent CTA walks ~7 work items through all three
+    fused residual blocks, weight ring and barriers wrapping many times) against the same positions
+    evaluated 192 at a time (one item per CTA): a board's result must not depend on the batch it is in."""
+    game = make_game(name, g)
+    sd = synthetic_state_dict(game, 128, 3, 128, seed=21, conv_gain=1.0, fc_scale=1.0)
+    states = random_positions(game, 4096, seed=8)
+    p = [s[0] for s in states]; f = [s[1] for s in states]; s2 = [s[2] for s in states]
+    big = device_net(name, g, 128, 3, 128, sd, "bf16", max_batch=4096)
+    small = device_net(name, g, 128, 3, 128, sd, "bf16", max_batch=192)
+    v_big, p_big = big.evaluate(p, f, s2)
+    for lo in range(0, 4096, 192):
+        hi = min(lo + 192, 4096)
+        v, pr = small.evaluate(p[lo:hi], f[lo:hi], s2[lo:hi])
+        np.testing.assert_array_equal(v, v_big[lo:hi])
+        np.testing.assert_array_equal(pr, p_big[lo:hi])
+    # and the whole batch agrees with the torch-fp32 oracle on a sample
+    idx = list(range(0, 4096, 97))
+    want_v, want_p = onet.evaluate_batch(game, sd, [states[i] for i in idx])
+    np.testing.assert_allclose(p_big[idx], want_p, atol=BF16_ATOL, rtol=0)
+    np.testing.assert_allclose(v_big[idx], want_v, atol=BF16_ATOL, rtol=0)
