@@ -477,8 +477,6 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                      (int)netk::resblock_smem_bytes<8>()));
         DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::resblock_smem_bytes<7>()));
-        DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_sparse, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((27 * C + C + 16 * C) * sizeof(float) + netk::kEncode2Boards * (g + 2) * (g + 2) + 16)));
         DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");
         DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)((size_t)P0 * H * sizeof(float))));

@@ -10,12 +10,24 @@
 // (SBO = 128 B per 8-row group, LBO = rows * 16 B per K chunk).  Because row pitch is uniform,
 // the A operand of tap (dy, dx) is the SAME shared-memory image read from a start address
 // shifted by (dy*Wp + dx) rows -- no im2col copies, one activation load per CTA.
-//   GEMM per CTA: M = 4 tiles x 128 rows, N = 128, K = 9 taps x 128 channels.
-//   A  : 512 + 2*halo rows x 128 ch, one cp.async.bulk per channel chunk (16 copies)
-//   B  : per tap a pre-packed 32 KB weight image, double buffered (cp.async.bulk)
-//   D  : 4 x (128 lanes x 128 columns) fp32 = all 512 TMEM columns
-// Warp roles: warp 0 bulk-copy producer, warp 1 TMEM allocator + MMA issuer, warps 2-5
-// epilogue (tcgen05.ld -> bias / residual / ReLU -> bf16 -> coalesced 16-byte stores).
+//
+// Kernels in this file, newest last (all share the PTX wrappers and descriptors below):
+//   k_conv3x3_tc      first version: one CTA per 512 rows, load -> 9x16 MMAs -> epilogue in sequence.
+//                     Kept selectable (DM_CONV_V1=1) as the A/B baseline of profiles/README.md.
+//   k_conv3x3_tc2     persistent CTA per SM, warp-specialised (weight ring, activation producer, MMA
+//                     issuer, 4 epilogue warps), double-buffered activation windows and TMEM
+//                     accumulators.  Runs the policy-head conv, and the trunk of board sizes other
+//                     than 7 and 8.  <kPair = true> reads/writes the pad-free pair layout of 8x8 boards.
+//   k_resblock_tc<G>  whole residual blocks (conv -> ReLU -> conv -> + skip -> ReLU) with the
+//                     intermediate activation in shared memory, and all blocks of the trunk in one
+//                     launch; G = 8 (pair layout) and G = 7 (flat layout, 64 rows per board).  This
+//                     is the dominant kernel of the engine.
+//   k_policy_fc_tc    policy-head FC as a split-K tcgen05 GEMM;  k_heads_finish: value head FCs,
+//                     softmax, legality mask (GameNet.evaluate's post-processing).
+// Timing-experiment switches (never set in the shipped build; each removes work to bound what an
+// optimisation could gain, results are wrong by construction): DM_EXPERIMENT_ALIGNED,
+// DM_EXP_NOEPI, DM_EXP_NOSTORE, DM_EXP_NOWEIGHTS -- the numbers they produced are in
+// profiles/README.md.
 #pragma once
 #include <cuda_bf16.h>
 
@@ -539,18 +551,11 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
 #endif
                 // prefetch this row's residual (all 128 channels) before waiting for the tensor core
                 uint4 res[kChunks];
-#ifdef DM_EXP_NORES
-                if (args.residual && valid) {
-#pragma unroll
-                    for (int kc = 0; kc < kChunks; ++kc) res[kc] = make_uint4(kc, m, kc, m);   // timing experiment: no residual loads
-                }
-#else
                 if (args.residual && valid) {
 #pragma unroll
                     for (int kc = 0; kc < kChunks; ++kc)
                         res[kc] = *reinterpret_cast<const uint4*>(args.residual + ((size_t)kc * args.rows_total + m) * 8);
                 }
-#endif
                 if (!waited) {
                     mbar_wait(bar_accfull + 8 * buf, (j >> 1) & 1);
                     tc_fence_after();

@@ -133,110 +133,6 @@ __global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const 
     }
 }
 
-// Same computation for the bf16 path, exploiting that the input planes are binary: the output
-// of the first convolution is  bias + [FIRST to move] * (sum of the in-board player-plane taps)
-// + sum over occupied neighbour cells of one weight row.  A cell is own, opponent or empty, so
-// at most 9 (on average ~4) 8-channel rows are added per output instead of 27 multiply-adds.
-// Requires C % 8 == 0.  Cell codes: 0 empty / off-board, 1 mover's stone, 2 opponent's.
-constexpr int kEncode2Boards = 8;
-__global__ void __launch_bounds__(256) k_encode_conv1_sparse(GameCfg cfg, int n, const int* count_dev,
-                                                             const u64* first, const u64* second, const u8* player,
-                                                             const float* __restrict__ w,
-                                                             const float* __restrict__ bias, int C,
-                                                             __nv_bfloat16* out_bf16, size_t rows_total) {
-    extern __shared__ __align__(16) float smem[];
-    const int g = cfg.g, gp = g + 2, P0 = g * g;
-    float* s_w = smem;             // [27][C]
-    float* s_b = s_w + 27 * C;     // [C]
-    float* s_pl = s_b + C;         // [16 border classes][C]: summed player-plane taps
-    u8* s_code = reinterpret_cast<u8*>(s_pl + 16 * C);  // [kEncode2Boards][gp*gp]
-    __shared__ int s_player[kEncode2Boards];
-    const int live = live_count(count_dev, n);
-    const int b0 = blockIdx.x * kEncode2Boards;
-    if (b0 >= live) return;
-    for (int i = threadIdx.x; i < 27 * C; i += blockDim.x) s_w[i] = w[i];
-    for (int i = threadIdx.x; i < C; i += blockDim.x) s_b[i] = bias[i];
-    for (int i = threadIdx.x; i < kEncode2Boards * gp * gp; i += blockDim.x) {
-        int bb = i / (gp * gp), r = i % (gp * gp);
-        int b = b0 + bb;
-        u8 code = 0;
-        int y = r / gp - 1, x = r % gp - 1;
-        if (b < live && y >= 0 && y < g && x >= 0 && x < g) {
-            int pl = player[b];
-            bool transpose = (cfg.game == DM_HEX || cfg.game == DM_HEX_SWAP) && pl == 0;
-            int bit = transpose ? (x * g + y) : (y * g + x);
-            u64 f = first[b], s2 = second[b];
-            u64 own = pl ? f : s2, opp = pl ? s2 : f;
-            code = ((own >> bit) & 1) ? 1 : (((opp >> bit) & 1) ? 2 : 0);
-        }
-        s_code[i] = code;
-    }
-    if (threadIdx.x < kEncode2Boards) s_player[threadIdx.x] = (b0 + threadIdx.x < live) ? player[b0 + threadIdx.x] : 0;
-    __syncthreads();
-    // player-plane sums per border class: class = (y > 0) + 2*(y < g-1) + 4*((x > 0) + 2*(x < g-1))
-    for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
-        int cls = i / C, c = i % C;
-        int ym = cls & 3, xm = cls >> 2;
-        float acc = 0.f;
-        for (int tap = 0; tap < 9; ++tap) {
-            int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            bool yin = dy == 0 || (dy < 0 ? (ym & 1) : (ym & 2));
-            bool xin = dx == 0 || (dx < 0 ? (xm & 1) : (xm & 2));
-            if (yin && xin) acc += s_w[(tap * 3 + 2) * C + c];
-        }
-        s_pl[i] = acc;
-    }
-    __syncthreads();
-    const RowGeom geom = RowGeom::make(g);
-    const int chunks = C / 8;
-    // thread -> (position, chunk phase): lanes of a warp own consecutive positions, so every
-    // 16-byte store of a warp lands in one contiguous run of rows; no per-item divisions.
-    const int pos = threadIdx.x & 63, q = threadIdx.x >> 6;  // blockDim = 256 -> q in 0..3
-    if (pos >= P0) return;
-    const int y = pos / g, x = pos % g;
-    const int cls = (y > 0) + 2 * (y < g - 1) + 4 * ((x > 0) + 2 * (x < g - 1));
-    for (int bb = 0; bb < kEncode2Boards; ++bb) {
-        const int b = b0 + bb;
-        if (b >= live) break;
-        const u8* code = s_code + bb * gp * gp;
-        int cd[9];
-#pragma unroll
-        for (int tap = 0; tap < 9; ++tap) cd[tap] = code[(y + tap / 3) * gp + (x + tap % 3)];
-        const bool first_to_move = s_player[bb] != 0;
-        const size_t row = (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
-        for (int kc = q; kc < chunks; kc += 4) {
-            float4 a0 = *reinterpret_cast<const float4*>(s_b + kc * 8);
-            float4 a1 = *reinterpret_cast<const float4*>(s_b + kc * 8 + 4);
-            if (first_to_move) {
-                const float4 p0 = *reinterpret_cast<const float4*>(s_pl + cls * C + kc * 8);
-                const float4 p1 = *reinterpret_cast<const float4*>(s_pl + cls * C + kc * 8 + 4);
-                a0.x += p0.x; a0.y += p0.y; a0.z += p0.z; a0.w += p0.w;
-                a1.x += p1.x; a1.y += p1.y; a1.z += p1.z; a1.w += p1.w;
-            }
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-                if (cd[tap]) {
-                    const float* wr = s_w + (tap * 3 + cd[tap] - 1) * C + kc * 8;
-                    const float4 w0 = *reinterpret_cast<const float4*>(wr);
-                    const float4 w1 = *reinterpret_cast<const float4*>(wr + 4);
-                    a0.x += w0.x; a0.y += w0.y; a0.z += w0.z; a0.w += w0.w;
-                    a1.x += w1.x; a1.y += w1.y; a1.z += w1.z; a1.w += w1.w;
-                }
-            }
-            __nv_bfloat162 q0 = __floats2bfloat162_rn(fmaxf(a0.x, 0.f), fmaxf(a0.y, 0.f));
-            __nv_bfloat162 q1 = __floats2bfloat162_rn(fmaxf(a0.z, 0.f), fmaxf(a0.w, 0.f));
-            __nv_bfloat162 q2 = __floats2bfloat162_rn(fmaxf(a1.x, 0.f), fmaxf(a1.y, 0.f));
-            __nv_bfloat162 q3 = __floats2bfloat162_rn(fmaxf(a1.z, 0.f), fmaxf(a1.w, 0.f));
-            uint4 v;
-            v.x = *reinterpret_cast<u32*>(&q0);
-            v.y = *reinterpret_cast<u32*>(&q1);
-            v.z = *reinterpret_cast<u32*>(&q2);
-            v.w = *reinterpret_cast<u32*>(&q3);
-            *reinterpret_cast<uint4*>(out_bf16 + ((size_t)kc * rows_total + row) * 8) = v;
-        }
-    }
-}
-
 // Table-driven variant (the one the bf16 path runs): because every input cell is own / opponent /
 // empty, the contribution of one board row to an output is a function of just 3 cells = 27
 // patterns.  The host folds the weights into  tab[dy][pattern][C]  (pattern = c(x-1) + 3 c(x) +

@@ -107,7 +107,9 @@ struct PoolView {
 
 // ------------------------------------------------------------------ small warp helpers
 __device__ __forceinline__ void count(const PoolView& P, int which, unsigned long long v) {
+#ifndef DM_EXP_NOCOUNT   // timing experiment: how much of the tree kernels is the shared counters
     if (v) atomicAdd(&P.counters[which], v);
+#endif
 }
 
 __device__ __forceinline__ GState root_state(const PoolView& P, int t) {
