@@ -40,6 +40,29 @@ static inline GameCfg make_game_cfg(int game, int grid) {
     return c;
 }
 
+// The same configuration as compile-time constants: with GAME / G known the compiler folds every
+// shift amount and mask of the bitboard code and unrolls the ray loops (the hot tree kernels are
+// instantiated for the BASELINE board sizes; the generic kernels read the runtime GameCfg).
+template <int GAME, int G>
+__device__ __forceinline__ GameCfg const_game_cfg() {
+    GameCfg c;
+    c.game = GAME;
+    c.g = G;
+    c.cells = G * G;
+    c.num_actions = G * G + ((GAME == DM_HEX_SWAP || GAME == DM_OTHELLO) ? 1 : 0);
+    c.full = (G * G == 64) ? ~0ull : ((1ull << (G * G)) - 1);
+    u64 col0 = 0;
+#pragma unroll
+    for (int y = 0; y < G; ++y) col0 |= 1ull << (y * G);
+    c.col0 = col0;
+    c.colL = col0 << (G - 1);
+    c.not_col0 = c.full & ~c.col0;
+    c.not_colL = c.full & ~c.colL;
+    c.row0 = (1ull << G) - 1;
+    c.rowL = c.row0 << (G * (G - 1));
+    return c;
+}
+
 static inline bool game_cfg_valid(int game, int grid) {
     switch (game) {
         case DM_TICTACTOE: return true;

@@ -296,10 +296,19 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     int ph = prof_begin(net, 2, st);
     netk::k_policy_fc_tc<<<dim3((n + 127) / 128, net->fc_split), netk::kFcThreads, netk::fc_smem_bytes(net->fc_na), st>>>(fa);
     ++g_dm_launches;
-    netk::k_heads_finish<<<(n + netk::kFinishBoards - 1) / netk::kFinishBoards, netk::kFinishBoards * 32,
-                           (size_t)P0 * net->cfg.hidden * sizeof(float), st>>>(g, n, count_dev, first, second, player, net->fc_partial,
-                                                     net->fc_split, n_cap, net->fc_na, net->vplane, hp, mode,
-                                                     value_out, probs_out);
+    {
+        const int fb = (n + netk::kFinishBoards - 1) / netk::kFinishBoards, ft = netk::kFinishBoards * 32;
+        const size_t fs = (size_t)P0 * net->cfg.hidden * sizeof(float);
+#define DM_FINISH(GAME, G)                                                                                             \
+    netk::k_heads_finish<GAME, G><<<fb, ft, fs, st>>>(g, n, count_dev, first, second, player, net->fc_partial,          \
+                                                      net->fc_split, n_cap, net->fc_na, net->vplane, hp, mode, value_out, \
+                                                      probs_out)
+        if (g.game == DM_OTHELLO && g.g == 8) DM_FINISH(DM_OTHELLO, 8);
+        else if (g.game == DM_HEX && g.g == 7) DM_FINISH(DM_HEX, 7);
+        else if (g.game == DM_HEX_SWAP && g.g == 7) DM_FINISH(DM_HEX_SWAP, 7);
+        else DM_FINISH(-1, 0);
+#undef DM_FINISH
+    }
     prof_end(net, ph, st);
     DM_LAUNCH_CHECK();
     return DM_OK;
@@ -478,8 +487,13 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
         DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::resblock_smem_bytes<7>()));
         DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");
-        DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)P0 * H * sizeof(float))));
+        {
+            const int fs = (int)((size_t)P0 * H * sizeof(float));
+            DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish<-1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+            DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish<DM_OTHELLO, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+            DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish<DM_HEX, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+            DM_CUDA(cudaFuncSetAttribute(netk::k_heads_finish<DM_HEX_SWAP, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, fs));
+        }
         DM_CUDA(cudaFuncSetAttribute(netk::k_policy_fc_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::fc_smem_bytes(net->fc_na)));
         net->bf16_ready = true;

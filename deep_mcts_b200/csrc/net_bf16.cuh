@@ -1138,13 +1138,16 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_policy_fc_tc(FcArgs args) {
 // Sums the split-K partial logits, runs the value-head FCs and GameNet.evaluate's
 // post-processing (gamenet.py:67-85).  One warp per board.
 constexpr int kFinishBoards = 16;
-__global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg, int n, const int* count_dev, const u64* first,
+// GAME >= 0: instantiated for one (game, board size), so the legality mask's bitboard code has constant shifts.
+template <int GAME, int G>
+__global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg_in, int n, const int* count_dev, const u64* first,
                                                       const u64* second, const u8* player,
                                                       const float* __restrict__ partial, int split, int n_cap, int NA,
                                                       const float* __restrict__ vplane, HeadParams hp, int mode,
                                                       float* value_out, float* probs_out) {
     extern __shared__ __align__(16) float s_w1[];  // [P0][H] transposed value-FC1 weights
     __shared__ float s_vp[kFinishBoards][64];
+    const GameCfg cfg = GAME >= 0 ? const_game_cfg<(GAME >= 0 ? GAME : 0), (G > 0 ? G : 8)>() : cfg_in;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gb = blockIdx.x * kFinishBoards + warp;
     const int P0 = cfg.g * cfg.g, A = cfg.num_actions;

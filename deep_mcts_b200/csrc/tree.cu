@@ -986,11 +986,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 // The pending leaf is read from the per-tree copy, because other warps of this launch are already
 // claiming slots of the next leaf batch; the evaluator outputs (indexed by the OLD slot) are not
 // touched by this kernel.  Saves a kernel boundary per round and finds the path's nodes cache-hot.
-template <bool kSelfPlay, typename PriorT>
+// GAME >= 0: instantiated for one (game, board size) with the rules' masks and shifts as constants.
+template <bool kSelfPlay, typename PriorT, int GAME, int G>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
-    k_round(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
+    k_round(PoolView Pin, const PriorT* priors, int stride, const PriorT* values) {
     __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
     __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    PoolView P = Pin;
+    if (GAME >= 0) P.cfg = const_game_cfg<(GAME >= 0 ? GAME : 0), (G > 0 ? G : 8)>();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
     if (t >= P.n_trees) return;
@@ -1002,6 +1005,20 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
         expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
     }
     select_tree<kSelfPlay>(P, t, lane, s_path[warp]);
+}
+
+template <bool kSelfPlay, typename PriorT>
+static void launch_round(const PoolView& v, int blocks, int threads, cudaStream_t st, const PriorT* priors, int stride,
+                         const PriorT* values) {
+    const int game = v.cfg.game, g = v.cfg.g;
+    if (game == DM_OTHELLO && g == 8)
+        k_round<kSelfPlay, PriorT, DM_OTHELLO, 8><<<blocks, threads, 0, st>>>(v, priors, stride, values);
+    else if (game == DM_HEX && g == 7)
+        k_round<kSelfPlay, PriorT, DM_HEX, 7><<<blocks, threads, 0, st>>>(v, priors, stride, values);
+    else if (game == DM_HEX_SWAP && g == 7)
+        k_round<kSelfPlay, PriorT, DM_HEX_SWAP, 7><<<blocks, threads, 0, st>>>(v, priors, stride, values);
+    else
+        k_round<kSelfPlay, PriorT, -1, 0><<<blocks, threads, 0, st>>>(v, priors, stride, values);
 }
 
 // ---------------------------------------------------------------- virtual-loss mode
@@ -1555,11 +1572,11 @@ extern "C" int dm_pool_round(dm_pool* p, const void* priors, int stride, const v
     DM_CUDA(cudaMemsetAsync(p->v.leaf_count, 0, sizeof(int), st));
     const int blocks = tree_blocks(p->v.n_trees), threads = kWarpsPerBlock * 32;
     if (is_f64) {
-        if (selfplay) k_round<true, double><<<blocks, threads, 0, st>>>(p->v, (const double*)priors, stride, (const double*)values);
-        else k_round<false, double><<<blocks, threads, 0, st>>>(p->v, (const double*)priors, stride, (const double*)values);
+        if (selfplay) launch_round<true, double>(p->v, blocks, threads, st, (const double*)priors, stride, (const double*)values);
+        else launch_round<false, double>(p->v, blocks, threads, st, (const double*)priors, stride, (const double*)values);
     } else {
-        if (selfplay) k_round<true, float><<<blocks, threads, 0, st>>>(p->v, (const float*)priors, stride, (const float*)values);
-        else k_round<false, float><<<blocks, threads, 0, st>>>(p->v, (const float*)priors, stride, (const float*)values);
+        if (selfplay) launch_round<true, float>(p->v, blocks, threads, st, (const float*)priors, stride, (const float*)values);
+        else launch_round<false, float>(p->v, blocks, threads, st, (const float*)priors, stride, (const float*)values);
     }
     DM_LAUNCH_CHECK();
     return DM_OK;
