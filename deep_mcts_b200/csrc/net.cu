@@ -26,7 +26,7 @@ struct dm_net {
     size_t rows_total = 0;
     // fp32 weights
     float *conv1_w = nullptr, *conv1_b = nullptr;
-    float *conv1_tab = nullptr, *conv1_base = nullptr;  // k_encode_conv1_table operands
+    __half* conv1_tab16 = nullptr;  // k_encode_conv1_table operand: padded fp16 table image
     std::vector<float*> trunk_w, trunk_b;
     float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_t = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
     float vconv_b = 0.f, vfc2_b = 0.f;
@@ -209,7 +209,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     const int enc3_groups = (n + netk::kEncode3Boards - 1) / netk::kEncode3Boards;
     const int enc3_blocks = std::min(enc3_groups, netk::kEncode3CtasPerSm * net->sm_count);
     netk::k_encode_conv1_table<<<enc3_blocks, 256, netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, first, second, player,
-                                                                         net->conv1_tab, net->conv1_base, C, net->a0,
+                                                                         net->conv1_tab16, C, net->a0,
                                                                          net->rows_total, net->pair_layout ? 1 : 0);
     prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
@@ -436,8 +436,14 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                         basev[((size_t)pl * 16 + cls) * C + c] = acc;
                     }
                 }
-            DM_TRY(net_upload(net, &net->conv1_tab, tab));
-            DM_TRY(net_upload(net, &net->conv1_base, basev));
+            // one padded fp16 image [tab rows | base rows][C + 8]: the kernel bulk-copies it into shared memory as is
+            const int CP = C + 8;
+            std::vector<__half> tab16((size_t)netk::kEncode3Rows * CP, __float2half(0.f));
+            for (int r = 0; r < 81; ++r)
+                for (int c = 0; c < C; ++c) tab16[(size_t)r * CP + c] = __float2half_rn(tab[(size_t)r * C + c]);
+            for (int r = 0; r < 32; ++r)
+                for (int c = 0; c < C; ++c) tab16[(size_t)(81 + r) * CP + c] = __float2half_rn(basev[(size_t)r * C + c]);
+            DM_TRY(net_upload(net, &net->conv1_tab16, tab16));
             DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)netk::encode3_smem_bytes(C, g)));
         }

@@ -384,6 +384,159 @@ __device__ __forceinline__ void mbar_arrive(u32 bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
+// ============================================================================================
+// First layer of the bf16 path: bitboards -> 3 input planes -> 3x3 conv (3 -> 128) + folded BN + ReLU
+// -> bf16 rows in the trunk's layout (reference <game>/convolutionalnet.py states_to_tensor +
+// convolutionalnet.py:76-89).  Because every input cell is own / opponent / empty, the contribution
+// of one board line to an output is a function of just 3 cells = 27 patterns: the host folds the
+// weights into  tab[dy][pattern][C]  (pattern = c(x-1) + 3 c(x) + 9 c(x+1)) and
+// base[player][border class][C]  (bias + the in-board taps of the constant player plane), so an
+// output chunk is four table reads: base + tab[-1] + tab[0] + tab[+1].
+// The kernel is bound by shared-memory bandwidth, so the tables are staged as fp16 (one 16-byte read
+// = one whole 8-channel chunk; entries are sums of at most 9 folded weights, the fp16 rounding of
+// 2^-11 relative per entry stays below the bf16 rounding of the output; sums accumulate in fp32).
+// Persistent CTAs: the 30 KB table image (built and padded on the host, rows +16 B so that lanes
+// reading DIFFERENT rows at the same column hit different banks) arrives with one bulk copy, then the
+// CTA walks groups of kEncode3Boards boards, prefetching the next group's bitboards.
+#ifndef DM_ENC_BOARDS
+#define DM_ENC_BOARDS 2
+#endif
+#ifndef DM_ENC_CTAS
+#define DM_ENC_CTAS 2
+#endif
+constexpr int kEncode3Boards = DM_ENC_BOARDS;
+constexpr int kEncode3CtasPerSm = DM_ENC_CTAS;
+constexpr int kEncode3Rows = 3 * 27 + 2 * 16;                 // table rows: tab then base
+__host__ __device__ inline size_t encode3_table_bytes(int C) { return (size_t)kEncode3Rows * (C + 8) * sizeof(__half); }
+inline size_t encode3_smem_bytes(int C, int g) {
+    return encode3_table_bytes(C) + (size_t)kEncode3Boards * (g + 2) * (g + 2) + 64;
+}
+__global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, const int* count_dev,
+                                                            const u64* first, const u64* second, const u8* player,
+                                                            const __half* __restrict__ tab16,   // [113][C + 8]
+                                                            int C, __nv_bfloat16* out_bf16, size_t rows_total,
+                                                            int pair_layout) {
+    extern __shared__ __align__(16) unsigned char smem_enc[];
+    __shared__ __align__(8) u64 s_bar;
+    __shared__ int s_player[kEncode3Boards];
+    const int g = cfg.g, gp = g + 2, P0 = g * g;
+    const int CP = C + 8;                // padded row pitch (halves)
+    __half* s_tab = reinterpret_cast<__half*>(smem_enc);   // [3*27][CP]
+    __half* s_base = s_tab + 81 * CP;                      // [2*16][CP]
+    u8* s_code = reinterpret_cast<u8*>(s_base + 32 * CP);
+    const int live = live_count(count_dev, n);
+    const int n_groups = (live + kEncode3Boards - 1) / kEncode3Boards;
+    if ((int)blockIdx.x >= n_groups) return;
+    const u32 bar = smem_u32(&s_bar);
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const u32 bytes = (u32)encode3_table_bytes(C);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(smem_u32(s_tab), tab16, bytes, bar);
+    }
+    // this thread's slot of the padded code grid never changes: (board in group, padded cell) -> bit index
+    const bool fills = (int)threadIdx.x < kEncode3Boards * gp * gp;
+    const int my_bb = fills ? (int)threadIdx.x / (gp * gp) : 0;
+    int my_bit = -1, my_bit_t = -1;
+    if (fills) {
+        const int r = (int)threadIdx.x % (gp * gp);
+        const int cy = r / gp - 1, cx = r % gp - 1;
+        if (cy >= 0 && cy < g && cx >= 0 && cx < g) {
+            my_bit = cy * g + cx;
+            my_bit_t = cx * g + cy;      // Hex nets see the transposed board when SECOND moves
+        }
+    }
+    const RowGeom geom = RowGeom::make(g);
+    const int pos = threadIdx.x & 63, q = threadIdx.x >> 6;
+    const int y = pos / g, x = pos % g;
+    const int cls = (y > 0) + 2 * (y < g - 1) + 4 * ((x > 0) + 2 * (x < g - 1));
+    const bool hex_like = (cfg.game == DM_HEX || cfg.game == DM_HEX_SWAP);
+    // bitboards of this thread's board in the first group
+    u64 nf = 0, ns = 0;
+    int npl = 0;
+    {
+        const int b = (int)blockIdx.x * kEncode3Boards + my_bb;
+        if (fills && b < live) {
+            nf = first[b];
+            ns = second[b];
+            npl = player[b];
+        }
+    }
+    bool tables_ready = false;
+    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
+        const int b0 = grp * kEncode3Boards;
+        const u64 f = nf, s2 = ns;
+        const int pl = npl;
+        {   // prefetch the next group's bitboards
+            const int b = (grp + (int)gridDim.x) * kEncode3Boards + my_bb;
+            if (fills && b < live) {
+                nf = first[b];
+                ns = second[b];
+                npl = player[b];
+            }
+        }
+        __syncthreads();   // the previous group's codes are no longer read
+        if (fills) {
+            u8 code = 0;
+            if (my_bit >= 0 && b0 + my_bb < live) {
+                const int bit = (hex_like && pl == 0) ? my_bit_t : my_bit;
+                const u64 own = pl ? f : s2, opp = pl ? s2 : f;
+                code = ((own >> bit) & 1) ? 1 : (((opp >> bit) & 1) ? 2 : 0);
+            }
+            s_code[threadIdx.x] = code;
+            if ((int)threadIdx.x % (gp * gp) == 0) s_player[my_bb] = pl;
+        }
+        __syncthreads();
+        if (!tables_ready) {
+            mbar_wait(bar, 0);
+            tables_ready = true;
+        }
+        if (pos >= P0) continue;
+#pragma unroll
+        for (int bb = 0; bb < kEncode3Boards; ++bb) {
+            const int b = b0 + bb;
+            if (b >= live) break;
+            const u8* code = s_code + bb * gp * gp + y * gp + x;   // top-left of the 3x3 window (padded coords)
+            const __half* t0 = s_tab + (0 * 27 + code[0] + 3 * code[1] + 9 * code[2]) * CP;
+            const __half* t1 = s_tab + (1 * 27 + code[gp] + 3 * code[gp + 1] + 9 * code[gp + 2]) * CP;
+            const __half* t2 = s_tab + (2 * 27 + code[2 * gp] + 3 * code[2 * gp + 1] + 9 * code[2 * gp + 2]) * CP;
+            const __half* bs = s_base + ((s_player[bb] ? 16 : 0) + cls) * CP;
+            // pair layout (8x8 boards): rows of two boards interleaved, 9 entries per board row
+            const size_t row = pair_layout ? pair_entry(b, y, x)
+                                           : (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
+            // C == kC on this path: the four chunks of this thread are unrolled so that all 16 table reads are in flight
+#pragma unroll
+            for (int k4 = 0; k4 < kChunks / 4; ++k4) {
+                const int kc = q + 4 * k4;
+                const uint4 r0 = *reinterpret_cast<const uint4*>(bs + kc * 8);
+                const uint4 r1 = *reinterpret_cast<const uint4*>(t0 + kc * 8);
+                const uint4 r2 = *reinterpret_cast<const uint4*>(t1 + kc * 8);
+                const uint4 r3 = *reinterpret_cast<const uint4*>(t2 + kc * 8);
+                const u32 w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
+                const u32 w2[4] = {r2.x, r2.y, r2.z, r2.w}, w3[4] = {r3.x, r3.y, r3.z, r3.w};
+                float a[8];
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&w0[h]));
+                    const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&w1[h]));
+                    const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(&w2[h]));
+                    const float2 v3 = __half22float2(*reinterpret_cast<const __half2*>(&w3[h]));
+                    a[2 * h + 0] = fmaxf((v0.x + v1.x) + (v2.x + v3.x), 0.f);
+                    a[2 * h + 1] = fmaxf((v0.y + v1.y) + (v2.y + v3.y), 0.f);
+                }
+                uint4 v;
+                v.x = pack_bf16(a[0], a[1]);
+                v.y = pack_bf16(a[2], a[3]);
+                v.z = pack_bf16(a[4], a[5]);
+                v.w = pack_bf16(a[6], a[7]);
+                *reinterpret_cast<uint4*>(out_bf16 + ((size_t)kc * rows_total + row) * 8) = v;
+            }
+        }
+    }
+    if (!tables_ready) mbar_wait(bar, 0);   // never leave with the bulk copy in flight
+}
+
 template <bool kPair>
 __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args) {
     extern __shared__ unsigned char smem_raw[];

@@ -133,121 +133,6 @@ __global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const 
     }
 }
 
-// Table-driven variant (the one the bf16 path runs): because every input cell is own / opponent /
-// empty, the contribution of one board row to an output is a function of just 3 cells = 27
-// patterns.  The host folds the weights into  tab[dy][pattern][C]  (pattern = c(x-1) + 3 c(x) +
-// 9 c(x+1)) and  base[player][border class][C]  (bias + the in-board taps of the constant player
-// plane), so an output chunk is 4 branch-free table reads: base + tab[-1] + tab[0] + tab[+1].
-// Persistent: a CTA stages the tables in shared memory once and then walks groups of
-// kEncode3Boards boards (two CTAs per SM; 4096 boards = 2048 groups = 6.9 per CTA).
-constexpr int kEncode3Boards = 2;
-constexpr int kEncode3CtasPerSm = 2;
-// The kernel is bound by shared-memory bandwidth (four table rows are read per output chunk), so the
-// tables are staged as fp16: one 16-byte read = one whole 8-channel chunk.  Entries are sums of at
-// most 9 folded weights; the fp16 rounding (2^-11 relative per entry, four entries per output) stays
-// below the bf16 rounding of the output itself.  Sums are accumulated in fp32.
-inline size_t encode3_smem_bytes(int C, int g) {
-    // table rows are padded by 16 bytes in shared memory: lanes of a warp read DIFFERENT rows (their
-    // 3-cell patterns differ) at the same column, and an unpadded row pitch would put all of them on
-    // the same banks
-    return (size_t)(3 * 27 + 2 * 16) * (C + 8) * sizeof(__half) + (size_t)kEncode3Boards * (g + 2) * (g + 2) + 64;
-}
-__global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, const int* count_dev,
-                                                            const u64* first, const u64* second, const u8* player,
-                                                            const float* __restrict__ tab,   // [3][27][C]
-                                                            const float* __restrict__ basev,  // [2][16][C]
-                                                            int C, __nv_bfloat16* out_bf16, size_t rows_total,
-                                                            int pair_layout) {
-    extern __shared__ __align__(16) unsigned char smem_enc[];
-    const int g = cfg.g, gp = g + 2, P0 = g * g;
-    const int CP = C + 8;                // padded row pitch (halves)
-    __half* s_tab = reinterpret_cast<__half*>(smem_enc);   // [3*27][CP]
-    __half* s_base = s_tab + 81 * CP;                      // [2*16][CP]
-    u8* s_code = reinterpret_cast<u8*>(s_base + 32 * CP);
-    __shared__ int s_player[kEncode3Boards];
-    const int live = live_count(count_dev, n);
-    const int n_groups = (live + kEncode3Boards - 1) / kEncode3Boards;
-    if ((int)blockIdx.x >= n_groups) return;
-    {
-        const int c4 = C / 4;
-        const float4* src = reinterpret_cast<const float4*>(tab);
-        for (int i = threadIdx.x; i < (81 + 32) * c4; i += blockDim.x) {
-            const int rowi = i / c4;
-            const float4 v = rowi < 81 ? __ldg(src + i) : __ldg(reinterpret_cast<const float4*>(basev) + (i - 81 * c4));
-            __half2* dst = reinterpret_cast<__half2*>(s_tab + rowi * CP + (i % c4) * 4);   // s_base follows s_tab
-            dst[0] = __floats2half2_rn(v.x, v.y);
-            dst[1] = __floats2half2_rn(v.z, v.w);
-        }
-    }
-    const RowGeom geom = RowGeom::make(g);
-    const int chunks = C / 8;
-    const int pos = threadIdx.x & 63, q = threadIdx.x >> 6;
-    const int y = pos / g, x = pos % g;
-    const int cls = (y > 0) + 2 * (y < g - 1) + 4 * ((x > 0) + 2 * (x < g - 1));
-    const bool hex_like = (cfg.game == DM_HEX || cfg.game == DM_HEX_SWAP);
-    for (int grp = blockIdx.x; grp < n_groups; grp += gridDim.x) {
-        const int b0 = grp * kEncode3Boards;
-        __syncthreads();   // the previous group's codes are no longer read
-        for (int i = threadIdx.x; i < kEncode3Boards * gp * gp; i += blockDim.x) {
-            int bb = i / (gp * gp), r = i % (gp * gp);
-            int b = b0 + bb;
-            u8 code = 0;
-            int cy = r / gp - 1, cx = r % gp - 1;
-            if (b < live && cy >= 0 && cy < g && cx >= 0 && cx < g) {
-                int pl = player[b];
-                bool transpose = hex_like && pl == 0;
-                int bit = transpose ? (cx * g + cy) : (cy * g + cx);
-                u64 f = first[b], s2 = second[b];
-                u64 own = pl ? f : s2, opp = pl ? s2 : f;
-                code = ((own >> bit) & 1) ? 1 : (((opp >> bit) & 1) ? 2 : 0);
-            }
-            s_code[i] = code;
-        }
-        if (threadIdx.x < kEncode3Boards) s_player[threadIdx.x] = (b0 + threadIdx.x < live) ? player[b0 + threadIdx.x] : 0;
-        __syncthreads();
-        if (pos >= P0) continue;
-#pragma unroll
-        for (int bb = 0; bb < kEncode3Boards; ++bb) {
-            const int b = b0 + bb;
-            if (b >= live) break;
-            const u8* code = s_code + bb * gp * gp + y * gp + x;   // top-left of the 3x3 window (padded coords)
-            const __half* t0 = s_tab + (0 * 27 + code[0] + 3 * code[1] + 9 * code[2]) * CP;
-            const __half* t1 = s_tab + (1 * 27 + code[gp] + 3 * code[gp + 1] + 9 * code[gp + 2]) * CP;
-            const __half* t2 = s_tab + (2 * 27 + code[2 * gp] + 3 * code[2 * gp + 1] + 9 * code[2 * gp + 2]) * CP;
-            const __half* bs = s_base + ((s_player[bb] ? 16 : 0) + cls) * CP;
-            // pair layout (8x8 boards, see net_bf16.cuh): rows of two boards interleaved, 9 entries per board row
-            const size_t row = pair_layout ? (size_t)18 + ((size_t)((b >> 1) * 9 + 1 + y) * 2 + (b & 1)) * 9 + x
-                                           : (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
-            for (int kc = q; kc < chunks; kc += 4) {
-                const uint4 r0 = *reinterpret_cast<const uint4*>(bs + kc * 8);
-                const uint4 r1 = *reinterpret_cast<const uint4*>(t0 + kc * 8);
-                const uint4 r2 = *reinterpret_cast<const uint4*>(t1 + kc * 8);
-                const uint4 r3 = *reinterpret_cast<const uint4*>(t2 + kc * 8);
-                const u32 w0[4] = {r0.x, r0.y, r0.z, r0.w}, w1[4] = {r1.x, r1.y, r1.z, r1.w};
-                const u32 w2[4] = {r2.x, r2.y, r2.z, r2.w}, w3[4] = {r3.x, r3.y, r3.z, r3.w};
-                float a[8];
-#pragma unroll
-                for (int h = 0; h < 4; ++h) {
-                    const float2 v0 = __half22float2(*reinterpret_cast<const __half2*>(&w0[h]));
-                    const float2 v1 = __half22float2(*reinterpret_cast<const __half2*>(&w1[h]));
-                    const float2 v2 = __half22float2(*reinterpret_cast<const __half2*>(&w2[h]));
-                    const float2 v3 = __half22float2(*reinterpret_cast<const __half2*>(&w3[h]));
-                    a[2 * h + 0] = fmaxf((v0.x + v1.x) + (v2.x + v3.x), 0.f);
-                    a[2 * h + 1] = fmaxf((v0.y + v1.y) + (v2.y + v3.y), 0.f);
-                }
-                __nv_bfloat162 q0 = __floats2bfloat162_rn(a[0], a[1]), q1 = __floats2bfloat162_rn(a[2], a[3]);
-                __nv_bfloat162 q2 = __floats2bfloat162_rn(a[4], a[5]), q3 = __floats2bfloat162_rn(a[6], a[7]);
-                uint4 v;
-                v.x = *reinterpret_cast<u32*>(&q0);
-                v.y = *reinterpret_cast<u32*>(&q1);
-                v.z = *reinterpret_cast<u32*>(&q2);
-                v.w = *reinterpret_cast<u32*>(&q3);
-                *reinterpret_cast<uint4*>(out_bf16 + ((size_t)kc * rows_total + row) * 8) = v;
-            }
-        }
-    }
-}
-
 // fp32 3x3 conv C -> C + bias (+ residual) + ReLU on NHWC activations, one block per board.
 // Thread item = (output channel, strip of up to 8 positions).
 __global__ void __launch_bounds__(256) k_conv3x3_f32(int g, int C, int n, const int* count_dev,
