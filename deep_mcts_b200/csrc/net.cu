@@ -295,7 +295,9 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     netk::FcArgs fa{net->t16, net->pfc_w16, net->fc_partial, P0, net->fc_na, net->fc_split, n, n_cap, count_dev};
     int ph = prof_begin(net, 2, st);
     netk::k_policy_fc_tc<<<dim3((n + 127) / 128, net->fc_split), netk::kFcThreads, netk::fc_smem_bytes(net->fc_na), st>>>(fa);
+    prof_end(net, ph, st);
     ++g_dm_launches;
+    ph = prof_begin(net, 3, st);
     {
         const int fb = (n + netk::kFinishBoards - 1) / netk::kFinishBoards, ft = netk::kFinishBoards * 32;
         const size_t fs = (size_t)P0 * net->cfg.hidden * sizeof(float);

@@ -148,11 +148,11 @@ class DeviceNet:
         _lib.call("dm_net_profile", self._h, 1 if enable else 0)
 
     def profile_read(self) -> dict:
-        """{class: (milliseconds, launches)} for 'encode', 'trunk_conv', 'heads' since profile(True)."""
+        """{class: (milliseconds, launches)} for 'encode', 'trunk_conv', 'policy_fc' (all heads on the fp32 path), 'heads_finish' since profile(True)."""
         ms = (_lib.c_double * 4)()
         launches = (_lib.c_int64 * 4)()
         _lib.call("dm_net_profile_read", self._h, ms, launches)
-        return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(("encode", "trunk_conv", "heads"))}
+        return {name: (float(ms[i]), int(launches[i])) for i, name in enumerate(("encode", "trunk_conv", "policy_fc", "heads_finish"))}
 
     # --------------------------------------------------------------------------- search
     def search_round(self, pool, selfplay: bool = False, timers: Optional[list] = None, fused: bool = False) -> None:

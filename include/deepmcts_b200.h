@@ -255,7 +255,8 @@ int dm_net_rollout_greedy(dm_net* net, int precision, int n, const uint64_t* fir
                           const uint64_t* second_dev, const uint8_t* player_dev, float* outcome_dev,
                           void* stream);
 /* CUDA-event timing of the network kernels on their launch stream, per kernel class:
- * [0] encode + first conv, [1] trunk 3x3 convs (the tcgen05 kernel at precision 1), [2] heads.
+ * [0] encode + first conv, [1] trunk 3x3 convs (the tcgen05 kernels at precision 1), [2] heads (bf16 path: the
+ * policy FC only), [3] heads finish (bf16 path).
  * dm_net_profile(net, 1) clears and starts, dm_net_profile_read synchronises and returns the
  * accumulated milliseconds and launch counts.  Used by bench.py for the roofline. */
 int dm_net_profile(dm_net* net, int enable);
