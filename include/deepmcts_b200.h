@@ -180,8 +180,10 @@ int dm_pool_expand_backup(dm_pool* pool, const void* priors_dev, int prior_strid
  * loop, mcts.py:119-138): every tree with a pending leaf expands it and backs it up from
  * values_dev / priors_dev (indexed by the slot the leaf was handed out in), then selects its next
  * leaf into the leaf buffers.  selfplay != 0 gives the selection dm_selfplay_select's move-making
- * (needs dm_selfplay_enable).  Exact mode only (leaves_per_round 1).  The evaluator outputs of the
- * previous batch must stay untouched until this call has run. */
+ * (needs dm_selfplay_enable) and a DENSE leaf batch: tree t's leaf is always in slot t and the leaf
+ * count is n_trees (a tree without a new leaf keeps its previous one there; its result is ignored),
+ * which removes the shared slot counter from the hot loop.  Exact mode only (leaves_per_round 1).
+ * The evaluator outputs of the previous batch must stay untouched until this call has run. */
 int dm_pool_round(dm_pool* pool, const void* priors_dev, int prior_stride, const void* values_dev, int is_f64,
                   int selfplay, void* stream);
 /* result of MCTS.step (mcts.py:139-148): visits_dev[n_trees][DM_MAX_ACTIONS] root child visit
