@@ -185,13 +185,46 @@ def format_cell(move: Action, board_size: int) -> str:
     return f"{chr(ord('a') + move % board_size)}{move // board_size + 1}"
 
 
-def net_from_argv(net_cls, board_size: int, needs_size: bool = True):
+def net_from_argv(net_cls, board_size: int):
     """``<interface> <board size> <checkpoint>``: load a .pth state_dict or a full checkpoint when the
     requested size matches, else a fresh network (othello/gtp_interface.py:38-46)."""
     if len(sys.argv) == 3 and board_size == int(sys.argv[1]):
         path = sys.argv[2]
         return net_cls.from_path(path, board_size) if path.endswith(".pth") else net_cls.from_path_full(path)
     return net_cls(board_size)
+
+
+def board_gtp_interface(name: str, net_cls, default_size: int, special_move: Optional[str] = None,
+                        hexgui: bool = False):
+    """The per-game engines differ in three facts: the network class, the name of the extra action
+    ``board_size ** 2`` ("pass" for Othello, "swap" for Hex with swap, none for Hex) and whether HexGui's
+    ``hexgui-analyze_commands`` probe is answered.  Returns the ``GTPInterface`` subclass."""
+
+    def parse_move(move: str, board_size: int) -> Action:
+        if special_move is not None and move.lower() == special_move:
+            return board_size ** 2
+        return parse_cell(move, board_size)
+
+    def format_move(move: Action, board_size: int) -> str:
+        if special_move is not None and move == board_size ** 2:
+            return special_move
+        return format_cell(move, board_size)
+
+    def __init__(self, board_size: int = default_size) -> None:
+        GTPInterface.__init__(self, board_size)
+        if hexgui:
+            self.commands["hexgui-analyze_commands"] = lambda args: None
+
+    body = {"__init__": __init__, "parse_move": staticmethod(parse_move), "format_move": staticmethod(format_move),
+            "get_game_net": staticmethod(lambda board_size: net_from_argv(net_cls, board_size)),
+            "default_size": default_size, "__doc__": f"GTP engine for {net_cls.__name__}."}
+    return type(name, (GTPInterface,), body)
+
+
+def run_engine(interface_cls) -> None:
+    """``python -m deep_mcts_b200.<game>.gtp_interface [<board size> <checkpoint>]``."""
+    size = int(sys.argv[1]) if len(sys.argv) == 3 else interface_cls.default_size
+    interface_cls(board_size=size).start()
 
 
 class GTPAgent(Agent):

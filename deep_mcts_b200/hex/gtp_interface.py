@@ -1,32 +1,8 @@
-"""Hex GTP engine (interface of reference deep_mcts/hex/gtp_interface.py)."""
-import sys
-from typing import List
-
-from ..game import Action
-from ..gtp_interface import GTPInterface, format_cell, net_from_argv, parse_cell
+"""Hex GTP engine, usable from HexGui (interface of reference deep_mcts/hex/gtp_interface.py)."""
+from ..gtp_interface import board_gtp_interface, run_engine
 from .convolutionalnet import ConvolutionalHexNet
 
-
-class HexGTPInterface(GTPInterface):
-    def __init__(self, board_size: int = 5) -> None:
-        super().__init__(board_size)
-        self.commands["hexgui-analyze_commands"] = self.analyze_commands
-
-    def analyze_commands(self, args: List[str]) -> None:
-        return None
-
-    @staticmethod
-    def parse_move(move: str, board_size: int) -> Action:
-        return parse_cell(move, board_size)
-
-    @staticmethod
-    def format_move(move: Action, board_size: int) -> str:
-        return format_cell(move, board_size)
-
-    @staticmethod
-    def get_game_net(board_size: int) -> ConvolutionalHexNet:
-        return net_from_argv(ConvolutionalHexNet, board_size)
-
+HexGTPInterface = board_gtp_interface("HexGTPInterface", ConvolutionalHexNet, default_size=5, hexgui=True)
 
 if __name__ == "__main__":
-    HexGTPInterface(board_size=int(sys.argv[1]) if len(sys.argv) == 3 else 5).start()
+    run_engine(HexGTPInterface)

@@ -1,50 +1,9 @@
-"""Othello policy/value net (interface of reference deep_mcts/othello/convolutionalnet.py:13-113)."""
-from typing import Any, Dict, Mapping, Optional, Sequence, Tuple
-
-import torch
-
-from ..convolutionalnet import ConvolutionalNet
-from ..game import GameManager, Player
-from ..gamenet import GameNet, _torch_load, planes_from_states
+"""Othello policy/value net: flat policy over the g*g cells plus "pass"
+(interface of reference deep_mcts/othello/convolutionalnet.py:13-113)."""
+from ..boardnet import BoardGameNet
 from .game import OthelloManager
 
-_SGD_DEFAULTS = {"lr": 0.01, "momentum": 0.9, "weight_decay": 0.001}
 
-
-class ConvolutionalOthelloNet(GameNet):
-    def __init__(self, grid_size: int, manager: Optional[GameManager] = None, optimizer_cls=torch.optim.SGD,
-                 optimizer_args: Tuple[Any, ...] = (), optimizer_kwargs: Mapping[str, Any] = _SGD_DEFAULTS,
-                 num_residual: int = 3, channels: int = 128, value_head_hidden_units: int = 128) -> None:
-        pass
-        super().__init__(
-            ConvolutionalNet(policy_features=grid_size ** 2 + 1, policy_shape=(grid_size ** 2 + 1,), grid_size=grid_size, in_channels=3,
-                             num_residual=num_residual, channels=channels,
-                             value_head_hidden_units=value_head_hidden_units),
-            manager if manager is not None else OthelloManager(grid_size), optimizer_cls, optimizer_args,
-            optimizer_kwargs)
-        self.grid_size = grid_size
-        self.num_residual = num_residual
-        self.channels = channels
-        self.value_head_hidden_units = value_head_hidden_units
-
-    def states_to_tensor(self, states: Sequence) -> torch.Tensor:
-        return planes_from_states(states, transpose_second=False)
-
-    def copy(self) -> "ConvolutionalOthelloNet":
-        twin = ConvolutionalOthelloNet(self.grid_size, self.manager, self.optimizer_cls, self.optimizer_args, self.optimizer_kwargs,
-                     self.num_residual, self.channels, self.value_head_hidden_units)
-        twin.load_state_dict(self.net.state_dict())
-        return twin
-
-    @classmethod
-    def from_path_full(cls, path: str, manager: Optional[GameManager] = None) -> "ConvolutionalOthelloNet":
-        blob = _torch_load(path, torch.device("cpu"))
-        net = cls(grid_size=blob["grid_size"], manager=manager, optimizer_cls=blob["optimizer_cls"], optimizer_args=blob["optimizer_args"],
-                  optimizer_kwargs=blob["optimizer_kwargs"], num_residual=blob["num_residual"],
-                  channels=blob["channels"], value_head_hidden_units=blob["value_head_hidden_units"])
-        net.load_state_dict(blob["state_dict"])
-        return net
-
-    def parameters(self) -> Dict[str, Any]:
-        return {**super().parameters(), "grid_size": self.grid_size, "num_residual": self.num_residual, "channels": self.channels,
-                "value_head_hidden_units": self.value_head_hidden_units}
+class ConvolutionalOthelloNet(BoardGameNet):
+    manager_cls = OthelloManager
+    extra_actions = 1

@@ -1,50 +1,18 @@
-"""Tic-tac-toe policy/value net, 3 channels by default (interface of reference deep_mcts/tictactoe/convolutionalnet.py:13-107)."""
-from typing import Any, Dict, Mapping, Optional, Sequence, Tuple
+"""Tic-tac-toe policy/value net: fixed 3x3 board, [3, 3] policy, 3 channels unless told otherwise
+(interface of reference deep_mcts/tictactoe/convolutionalnet.py:13-107; unlike the other nets its
+constructor has no grid-size argument)."""
+from typing import Any, Optional
 
-import torch
-
-from ..convolutionalnet import ConvolutionalNet
-from ..game import GameManager, Player
-from ..gamenet import GameNet, _torch_load, planes_from_states
+from ..boardnet import BoardGameNet
+from ..game import GameManager
 from .game import TicTacToeManager
 
-_SGD_DEFAULTS = {"lr": 0.01, "momentum": 0.9, "weight_decay": 0.001}
 
+class ConvolutionalTicTacToeNet(BoardGameNet):
+    manager_cls = TicTacToeManager
+    policy_as_grid = True
+    fixed_grid = 3
+    default_channels = 3
 
-class ConvolutionalTicTacToeNet(GameNet):
-    def __init__(self, manager: Optional[GameManager] = None, optimizer_cls=torch.optim.SGD,
-                 optimizer_args: Tuple[Any, ...] = (), optimizer_kwargs: Mapping[str, Any] = _SGD_DEFAULTS,
-                 num_residual: int = 3, channels: int = 3, value_head_hidden_units: int = 128) -> None:
-        grid_size = 3
-        super().__init__(
-            ConvolutionalNet(policy_features=9, policy_shape=(3, 3), grid_size=grid_size, in_channels=3,
-                             num_residual=num_residual, channels=channels,
-                             value_head_hidden_units=value_head_hidden_units),
-            manager if manager is not None else TicTacToeManager(), optimizer_cls, optimizer_args,
-            optimizer_kwargs)
-        self.grid_size = grid_size
-        self.num_residual = num_residual
-        self.channels = channels
-        self.value_head_hidden_units = value_head_hidden_units
-
-    def states_to_tensor(self, states: Sequence) -> torch.Tensor:
-        return planes_from_states(states, transpose_second=False)
-
-    def copy(self) -> "ConvolutionalTicTacToeNet":
-        twin = ConvolutionalTicTacToeNet(self.manager, self.optimizer_cls, self.optimizer_args, self.optimizer_kwargs,
-                     self.num_residual, self.channels, self.value_head_hidden_units)
-        twin.load_state_dict(self.net.state_dict())
-        return twin
-
-    @classmethod
-    def from_path_full(cls, path: str, manager: Optional[GameManager] = None) -> "ConvolutionalTicTacToeNet":
-        blob = _torch_load(path, torch.device("cpu"))
-        net = cls(manager=manager, optimizer_cls=blob["optimizer_cls"], optimizer_args=blob["optimizer_args"],
-                  optimizer_kwargs=blob["optimizer_kwargs"], num_residual=blob["num_residual"],
-                  channels=blob["channels"], value_head_hidden_units=blob["value_head_hidden_units"])
-        net.load_state_dict(blob["state_dict"])
-        return net
-
-    def parameters(self) -> Dict[str, Any]:
-        return {**super().parameters(), "num_residual": self.num_residual, "channels": self.channels,
-                "value_head_hidden_units": self.value_head_hidden_units}
+    def __init__(self, manager: Optional[GameManager] = None, *args: Any, **kwargs: Any) -> None:
+        super().__init__(None, manager, *args, **kwargs)

@@ -65,3 +65,49 @@ def test_train_step_and_copy_and_checkpoint(tmp_path):
     for k, v in net.net.state_dict().items():
         assert torch.equal(v, loaded.net.state_dict()[k])
     assert set(net.parameters()) >= {"optimizer_cls", "state_dict", "grid_size", "channels"}
+
+
+@pytest.mark.parametrize("name,g,policy_shape", [("othello", 4, (17,)), ("hex", 4, (4, 4)), ("hex_with_swap", 4, (17,)),
+                                                  ("tictactoe", 3, (3, 3))])
+def test_every_game_net_copies_and_round_trips_through_a_full_checkpoint(tmp_path, name, g, policy_shape):
+    """copy() / save_full / from_path_full / parameters() of all four per-game nets (one shared body,
+    deep_mcts_b200/boardnet.py), with the reference's constructor conventions: positional grid size
+    for the board games, none for tic-tac-toe."""
+    net = build_net(name, g, 8, 1, 16)
+    with torch.no_grad():
+        value, logits = net.forward(torch.rand(5, 3, g, g))
+    assert value.shape == (5, 1) and tuple(logits.shape[1:]) == policy_shape
+    twin = net.copy()
+    assert type(twin) is type(net) and twin.manager is net.manager
+    path = str(tmp_path / "anet-0.tar")
+    net.save_full(path)
+    loaded = type(net).from_path_full(path, net.manager)
+    for other in (twin, loaded):
+        assert (other.channels, other.num_residual, other.value_head_hidden_units, other.grid_size) == (8, 1, 16, g)
+        for k, v in net.net.state_dict().items():
+            assert torch.equal(v, other.net.state_dict()[k])
+    keys = set(net.parameters())
+    assert keys >= {"optimizer_cls", "optimizer_args", "optimizer_kwargs", "state_dict", "num_residual", "channels",
+                    "value_head_hidden_units"}
+    assert ("grid_size" in keys) == (name != "tictactoe")     # the reference's tic-tac-toe net saves no grid size
+
+
+def test_hex_policy_is_transposed_back_for_second_to_move():
+    """Rows whose player plane says SECOND are fed a transposed board; forward() must hand their policy back
+    in board coordinates (reference hex/convolutionalnet.py:54-62, hex_with_swap/convolutionalnet.py:54-65)."""
+    from deep_mcts_b200.game import Player
+    for name, flat in (("hex", False), ("hex_with_swap", True)):
+        net = build_net(name, 4, 8, 1, 16)
+        planes = torch.rand(6, 3, 4, 4)
+        planes[:, 2] = torch.tensor([1., 0., 1., 0., 0., 1.]).view(6, 1, 1)
+        with torch.no_grad():
+            _, logits = net.forward(planes)
+            _, raw = net.net(planes)
+        second = planes[:, 2, 0, 0] == int(Player.SECOND)
+        if flat:
+            assert torch.equal(logits[:, 16], raw[:, 16])                        # the swap logit is not moved
+            board, raw_board = logits[:, :16].reshape(6, 4, 4), raw[:, :16].reshape(6, 4, 4)
+        else:
+            board, raw_board = logits, raw
+        assert torch.equal(board[~second], raw_board[~second])
+        assert torch.equal(board[second], raw_board[second].transpose(1, 2))
