@@ -56,7 +56,7 @@ def ncu_dram_traffic_per_launch():
     launch) from the committed `ncu --set full` capture (profiles/), averaged over the captured launches;
     None if absent."""
     import csv
-    path = ROOT / "profiles" / "r1e_round_kernels_ncu_full_raw.csv"
+    path = ROOT / "profiles" / "r1g_round_kernels_ncu_full_raw.csv"
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -372,7 +372,7 @@ def run_b200(args):
                 "frac": achieved / peak_tflops if peak_tflops else None,
                 "traffic": ncu_dram_traffic_per_launch() if wl["game"] == "othello" and args.trees == 4096 else None,
                 "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch = three residual blocks (ncu --set full, "
-                                "profiles/r1e_round_kernels_ncu_full_raw.csv; the blocks' intermediate activations "
+                                "profiles/r1g_round_kernels_ncu_full_raw.csv; the blocks' intermediate activations "
                                 "are re-read from the 126 MB L2)",
                 # per fused residual block: the block input is read once (it is also the skip operand) and the
                 # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets; a launch
