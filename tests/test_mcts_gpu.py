@@ -373,3 +373,54 @@ def test_arena_compaction_preserves_exactness(name, g, kind):
     c = small.pool.counters()
     assert c["compactions"] >= 2 and c["capacity_errors"] == 0, c
     assert c["children_created"] > small.pool._search.num_simulations  # far more nodes created than the arena holds
+
+
+@pytest.mark.parametrize("name,g", [("othello", 8), ("hex", 7), ("hex_with_swap", 7), ("othello", 6)])
+def test_fused_round_stepped_search_matches_oracle(name, g):
+    """MCTS.step driven through dm_pool_round (expand/backup of the previous batch + next selection in one
+    launch; the BASELINE board sizes run the per-game kernel instances) with a host evaluator: visit counts,
+    stats and child order must equal the oracle's, move after move with subtree reuse."""
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200.pool import TreePool
+    from test_selfplay_gpu import evaluate_leaves
+    game = make_game(name, g)
+    manager = manager_for(name, g)
+    sims, T = 40, 5
+    pool = TreePool(manager, T, 1 << 15, seed=2)
+    pool.configure(sims, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, 0, 0.0, 0.25)
+    # distinct openings
+    rs = np.random.RandomState(3)
+    openings = []
+    for t in range(T):
+        s = game.initial_state()
+        for _ in range(t):
+            legal = game.legal_list(s)
+            s = game.child(s, legal[rs.randint(len(legal))])
+        openings.append(s)
+    pool.set_root_states(np.array([o[0] for o in openings], np.uint8), np.array([o[1] for o in openings], np.uint64),
+                         np.array([o[2] for o in openings], np.uint64))
+    refs = []
+    for o in openings:
+        r = OracleMCTS(game, sims, None, oev.hashed)
+        r.set_root_state(o)
+        refs.append(r)
+    for move in range(3):
+        pool.begin_step()
+        pool.select()
+        pri, val = evaluate_leaves(pool, game, oev.hashed, int(pool.leaf_count.item()))
+        for _ in range(sims):
+            pool.round(pri, val, selfplay=False)
+            pri, val = evaluate_leaves(pool, game, oev.hashed, int(pool.leaf_count.item()))
+        pool.expand_backup(pri, val)
+        visits, stats = pool.root_visits()
+        order, count, root_visits = pool.root_children()
+        actions = np.zeros(T, np.int32)
+        for t, ref in enumerate(refs):
+            _, ref_stats = ref.step()
+            assert [int(v) for v in visits[t]][: game.num_actions] == ref.root_visit_counts(), (t, move)
+            assert tuple(stats[t]) == tuple(ref_stats)
+            assert [int(a) for a in order[t, : count[t]]] == ref.root_children_actions()
+            actions[t] = int(np.argmax(visits[t]))
+            ref.advance(int(actions[t]))
+        pool.advance(actions)
+    assert pool.counters()["capacity_errors"] == 0

@@ -14,11 +14,8 @@ pytestmark = pytest.mark.gpu
 from test_games_gpu import manager_for  # noqa: E402
 
 
-def host_round(pool, game, evaluator):
-    """One self-play round with a HOST evaluator plugged into the leaf exchange."""
+def evaluate_leaves(pool, game, evaluator, n):
     from deep_mcts_b200 import _lib
-    pool.selfplay_select()
-    n = int(pool.leaf_count.item())
     T = pool.n_trees
     pri = np.zeros((T, _lib.DM_MAX_ACTIONS), np.float64)
     val = np.zeros(T, np.float64)
@@ -30,12 +27,29 @@ def host_round(pool, game, evaluator):
             v, probs = evaluator(game, (int(p[i]), int(f[i]), int(s[i])))
             val[i] = v
             pri[i, : game.num_actions] = probs
-    pool.expand_backup(torch.from_numpy(pri).to(pool.device), torch.from_numpy(val).to(pool.device))
-    return n
+    return torch.from_numpy(pri).to(pool.device), torch.from_numpy(val).to(pool.device)
 
 
-@pytest.mark.parametrize("name,g,sims", [("othello", 6, 30), ("hex_with_swap", 4, 25), ("tictactoe", 3, 20)])
-def test_selfplay_games_match_oracle(name, g, sims):
+def host_round(pool, game, evaluator, carry=None):
+    """One self-play round with a HOST evaluator plugged into the leaf exchange.  ``carry`` (a dict)
+    selects the fused form: ONE tree launch expands the batch evaluated in the previous call and
+    selects the next one (dm_pool_round, dense slots: tree t's leaf is slot t)."""
+    if carry is None:
+        pool.selfplay_select()
+        pri, val = evaluate_leaves(pool, game, evaluator, int(pool.leaf_count.item()))
+        pool.expand_backup(pri, val)
+        return
+    if "pri" not in carry:
+        carry["pri"], carry["val"] = evaluate_leaves(pool, game, evaluator, 0)
+    pool.round(carry["pri"], carry["val"], selfplay=True)
+    assert int(pool.leaf_count.item()) == pool.n_trees
+    carry["pri"], carry["val"] = evaluate_leaves(pool, game, evaluator, pool.n_trees)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("name,g,sims", [("othello", 6, 30), ("hex_with_swap", 4, 25), ("tictactoe", 3, 20), ("othello", 8, 20),
+                                         ("hex", 7, 20)])
+def test_selfplay_games_match_oracle(name, g, sims, fused):
     from deep_mcts_b200 import _lib
     from deep_mcts_b200.pool import TreePool
     game = make_game(name, g)
@@ -50,8 +64,9 @@ def test_selfplay_games_match_oracle(name, g, sims):
     outcome = game.outcome(ref.state)
     plies = len(examples)
     # enough rounds for every tree to finish one game (+ slack for root expansions / terminal sims)
+    carry = {} if fused else None
     for _ in range(plies * (sims + 2) + 5):
-        host_round(pool, game, oev.hashed)
+        host_round(pool, game, oev.hashed, carry)
         if pool.counters()["games"] >= T:
             break
     c = pool.counters()
