@@ -187,20 +187,49 @@ class BatchedSelfPlay:
     def positions_written(self) -> int:
         return sum(int(pool.replay_written.item()) for pool in self.pools)
 
-    def sample_batch(self, batch_size: int, generator: Optional[torch.Generator] = None
+    def sample_batch(self, batch_size: int, generator: Optional[torch.Generator] = None,
+                     written: Optional[Sequence[int]] = None, skip_oldest: int = 0
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         """Uniform sample over the replay rings: (first, second, player, pi[B, A], z[B, 1]) on the device
-        (reference train.py:337-348 samples uniformly over positions)."""
-        sizes = [min(int(pool.replay_written.item()), pool.replay_capacity) for pool in self.pools]
-        total = sum(sizes)
+        (reference train.py:337-348 samples uniformly over positions).
+
+        ``written`` (positions written per pool, e.g. from ``positions_written_per_pool()`` at a moment
+        when self-play was idle) restricts the sample to positions that were complete at that moment;
+        ``skip_oldest`` additionally leaves out that many of each ring's oldest positions -- the ones
+        self-play may be overwriting while the sample is taken on another stream."""
+        if written is None:
+            written = self.positions_written_per_pool()
+        dev = self.pool.device
+        A = self.pool.num_actions
+        parts = []
+        for pool, w in zip(self.pools, written):
+            cap = pool.replay_capacity
+            n = min(int(w), cap)
+            if n <= 0:
+                continue
+            if w > cap and skip_oldest > 0:
+                # ring is full: slots [head, head + skip) are the next to be overwritten
+                head = int(w) % cap
+                keep = torch.arange(n, device=dev)
+                keep = keep[((keep - head) % cap) >= min(skip_oldest, cap - 1)]
+            else:
+                keep = torch.arange(n, device=dev)
+            parts.append((pool, keep))
+        total = sum(int(k.numel()) for _, k in parts)
         if total == 0:
             raise RuntimeError("replay ring is empty")
-        dev = self.pool.device
         idx = torch.randint(0, total, (batch_size,), device=dev, generator=generator)
-        A = self.pool.num_actions
-        first = torch.cat([p.replay_first[:n] for p, n in zip(self.pools, sizes)])
-        second = torch.cat([p.replay_second[:n] for p, n in zip(self.pools, sizes)])
-        player = torch.cat([p.replay_player[:n] for p, n in zip(self.pools, sizes)])
-        pi = torch.cat([p.replay_pi[:n, :A] for p, n in zip(self.pools, sizes)])
-        z = torch.cat([p.replay_z[:n] for p, n in zip(self.pools, sizes)])
+        if len(parts) == 1:
+            pool, keep = parts[0]
+            sel = keep[idx]
+            return (pool.replay_first[sel], pool.replay_second[sel], pool.replay_player[sel], pool.replay_pi[sel, :A],
+                    pool.replay_z[sel].unsqueeze(1))
+        first = torch.cat([p.replay_first[k] for p, k in parts])
+        second = torch.cat([p.replay_second[k] for p, k in parts])
+        player = torch.cat([p.replay_player[k] for p, k in parts])
+        pi = torch.cat([p.replay_pi[k, :A] for p, k in parts])
+        z = torch.cat([p.replay_z[k] for p, k in parts])
         return first[idx], second[idx], player[idx], pi[idx], z[idx].unsqueeze(1)
+
+    def positions_written_per_pool(self):
+        return [int(pool.replay_written.item()) for pool in self.pools]

@@ -63,6 +63,7 @@ class TrainingConfiguration:
     train_steps_per_block: int = 8   # SGD steps after every block of num_simulations search rounds
     uniform_until_first_transfer: bool = True
     precision: Optional[str] = None
+    overlap_training: bool = True    # SGD steps run on their own stream while the next self-play block is searched
 
     def to_json_dict(self) -> Dict[str, Any]:
         d = asdict(self)
@@ -113,6 +114,10 @@ class SelfPlayTrainer:
         self.allreduce_ms = 0.0
         self.generator = torch.Generator(device=self.device)
         self.generator.manual_seed(1234 + self.rank)
+        self.engine.use_graph = True
+        self.sp_stream = torch.cuda.Stream(device=self.device) if config.overlap_training else None
+        self._sample_written = None      # replay positions that were complete when self-play was last idle
+        self._skip_oldest = 0
 
     # ---- self-play -------------------------------------------------------------------
     def _uniform_round(self) -> None:
@@ -135,18 +140,53 @@ class SelfPlayTrainer:
         else:
             self.engine.run_rounds(rounds)
 
+    def block(self, train_steps: int):
+        """One block of the loop: ``num_simulations`` search rounds for every game and ``train_steps`` SGD steps.
+        With ``overlap_training`` the two run concurrently on two streams: the steps sample only replay
+        positions that were complete when the block started (minus the ring slots this block's self-play may
+        overwrite), and the weight transfer happens at the block boundary, when both streams are idle.
+        Returns the list of (policy_loss, value_loss, accuracy) of the steps taken."""
+        if self.sp_stream is None or self.uniform_phase:
+            self.self_play_block()
+            return [self.train_step() for _ in range(train_steps)] if self.engine.positions_written() else []
+        main = torch.cuda.current_stream()
+        self._sample_written = self.engine.positions_written_per_pool()
+        # a block finishes at most one move per tree per (num_simulations + 1) rounds, and a few more for short games
+        self._skip_oldest = 2 * self.config.n_trees
+        self.sp_stream.wait_stream(main)
+        with torch.cuda.stream(self.sp_stream):
+            self.self_play_block()
+        losses = [self.train_step(defer_transfer=True) for _ in range(train_steps)] if sum(self._sample_written) else []
+        main.wait_stream(self.sp_stream)
+        self._sample_written = None
+        if self._transfer_due:
+            self._transfer_weights()
+        return losses
+
     # ---- training --------------------------------------------------------------------
-    def train_step(self):
-        first, second, player, pi, z = self.engine.sample_batch(self.config.batch_size, self.generator)
+    def train_step(self, defer_transfer: bool = False):
+        first, second, player, pi, z = self.engine.sample_batch(self.config.batch_size, self.generator,
+                                                                written=self._sample_written,
+                                                                skip_oldest=self._skip_oldest if self._sample_written else 0)
         planes = bitboards_to_planes(first, second, player, self.net.manager.board, self.transpose)
         if pi.shape[1:] != tuple(self.net.net.policy_head.out_shape):
             pi = pi.reshape(pi.shape[0], *self.net.net.policy_head.out_shape)
         losses = self.net.train(planes, pi, z)
         self.iterations += 1
         if self.iterations % self.config.transfer_interval == 0:
-            self.engine.sync_weights()   # weight transfer to the self-play kernels (train.py:169-171)
-            self.uniform_phase = False
+            if defer_transfer:
+                self._transfer_due = True    # the self-play stream is still using the current weights
+            else:
+                self._transfer_weights()
         return losses
+
+    _transfer_due = False
+
+    def _transfer_weights(self) -> None:
+        """Weight transfer to the self-play kernels (train.py:169-171)."""
+        self.engine.sync_weights()
+        self.uniform_phase = False
+        self._transfer_due = False
 
     def games_finished(self) -> int:
         return self.engine.counters()["games"]
@@ -166,11 +206,7 @@ def _train(game_net: GameNet, config: TrainingConfiguration) -> Iterable[Tuple[i
     target_games = max(1, config.num_games * config.nprocs // world)
     policy_loss = value_loss = acc = 0.0
     while trainer.games_finished() < target_games:
-        trainer.self_play_block()
-        if trainer.engine.positions_written() == 0:
-            continue
-        for _ in range(config.train_steps_per_block):
-            pl, vl, ac = trainer.train_step()
+        for pl, vl, ac in trainer.block(config.train_steps_per_block):
             policy_loss, value_loss, acc = (policy_loss + pl.detach().item(), value_loss + vl.detach().item(),
                                              acc + ac.detach().item())
             it = trainer.iterations

@@ -123,9 +123,7 @@ def train(rank, world):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(blocks):
-        tr.self_play_block()
-        for _ in range(cfg.train_steps_per_block):
-            tr.train_step()
+        tr.block(cfg.train_steps_per_block)     # self-play block and SGD steps, overlapped on two streams
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     c1 = tr.engine.counters()
@@ -141,7 +139,8 @@ def train(rank, world):
                           "sims_per_sec": sums["sims"] / maxima["s"],
                           "train_steps_per_sec": sums["steps"] / world / maxima["s"],
                           "gradient_allreduce_us": allreduce_us, "gradient_elements": n_elems,
-                          "train_steps_per_block": cfg.train_steps_per_block}))
+                          "train_steps_per_block": cfg.train_steps_per_block,
+                          "overlap_training": cfg.overlap_training}))
 
 
 def engines(rank, world):
