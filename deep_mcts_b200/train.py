@@ -14,7 +14,10 @@ is refreshed every ``transfer_interval`` iterations (169-171).
 
 Because device self-play is orders of magnitude faster than the reference's workers, the ratio
 of training iterations to self-play is explicit here (``train_steps_per_block``) instead of
-being whatever two free-running processes happened to produce.
+being whatever two free-running processes happened to produce.  Like the reference's two
+processes, the two halves run concurrently: the SGD steps of a block are issued on their own
+stream while the next self-play block is searched (``overlap_training``), sampling only replay
+positions that were complete when the block started.
 """
 import json
 import random
