@@ -140,3 +140,52 @@ def test_random_rollout_rates_within_binomial_bounds(name, g):
             p_gpu, p_cpu = float(np.mean(out == v)), float(np.mean(cpu == v))
             sigma = np.sqrt(max(p_gpu * (1 - p_gpu), 1e-4) * (1 / n_gpu + 1 / n_cpu))
             assert abs(p_gpu - p_cpu) < 5 * sigma + 1e-3, (name, s0, v, p_gpu, p_cpu)
+
+
+@pytest.mark.parametrize("name,g", [("tictactoe", 3), ("hex", 7), ("hex_with_swap", 7), ("othello", 8)])
+def test_device_game_logic_matches_reference_digest_over_100k_positions(golden_dir, name, g):
+    """The CUDA game engines against the reference's 100 000-position digests (tests/golden/digests.json):
+    the positions of the seeded walk are evaluated on the device in batches -- legal list order, set
+    (child) order, is_final, outcome and every child state -- and hashed in walk order."""
+    import hashlib
+    import json
+    import random
+    import sys
+    sys.path.insert(0, str(golden_dir))
+    from make_digests import absorb
+    pins = json.load(open(golden_dir / "digests.json"))
+    n_positions, checkpoints = max(pins["checkpoints"]), set(pins["checkpoints"])
+    game = make_game(name, g)
+    manager = manager_for(name, g)
+    # the walk (which move is played) needs only the sorted legal set; take it from the oracle
+    rng = random.Random(pins["seed"])
+    states = []
+    while len(states) < n_positions:
+        s = game.initial_state()
+        while len(states) < n_positions:
+            states.append(s)
+            if game.is_final(s):
+                break
+            choices = sorted(set(game.legal_list(s)))
+            s = game.child(s, choices[rng.randrange(len(choices))])
+    p = np.array([s[0] for s in states], np.uint8)
+    f = np.array([s[1] for s in states], np.uint64)
+    s2 = np.array([s[2] for s in states], np.uint64)
+    lst, order, cnt = manager.legal_batch(p, f, s2)
+    final, outcome = manager.status_batch(p, f, s2)
+    rep = np.repeat(np.arange(n_positions), cnt)
+    acts = np.concatenate([lst[i, : cnt[i]] for i in range(n_positions)]).astype(np.int32)
+    cp, cf, cs, ok = manager.child_batch(p[rep], f[rep], s2[rep], acts)
+    assert ok.all()
+    h = hashlib.sha256()
+    got = {}
+    edge = 0
+    for i in range(n_positions):
+        k = int(cnt[i])
+        children = [(int(cp[edge + j]), int(cf[edge + j]), int(cs[edge + j])) for j in range(k)]
+        edge += k
+        absorb(h, states[i], bool(final[i]), float(outcome[i]), [int(a) for a in lst[i, :k]],
+               [int(a) for a in order[i, :k]], children)
+        if i + 1 in checkpoints:
+            got[str(i + 1)] = h.hexdigest()
+    assert got == pins["digests"][f"{name}_{g}"]

@@ -123,3 +123,20 @@ def test_net_matches_reference(golden_dir, name, g, c):
     # north_star tolerance for fp32 network outputs: 1e-5 absolute
     np.testing.assert_allclose(value, z["value"], atol=1e-5, rtol=0)
     np.testing.assert_allclose(probs, z["probs"], atol=1e-5, rtol=0)
+
+
+@pytest.mark.parametrize("name,g", [("tictactoe", 3), ("hex", 7), ("hex_with_swap", 7), ("othello", 8)])
+def test_oracle_game_logic_matches_reference_digest_over_100k_positions(golden_dir, name, g):
+    """SHA-256 over 100 000 positions of seeded random playouts (state, is_final, outcome, legal list order,
+    set order, every child state) recorded from the unmodified reference managers
+    (tests/golden/make_digests.py): the oracle, driven through the same walk, must reproduce the digest at
+    every checkpoint."""
+    import sys
+    sys.path.insert(0, str(golden_dir))
+    from make_digests import walk_digest
+    pins = json.load(open(golden_dir / "digests.json"))
+    game = make_game(name, g)
+    got = walk_digest(game.initial_state, game.legal_list, game.children_order, game.child,
+                      lambda s: (game.is_final(s), game.outcome(s)), max(pins["checkpoints"]), tuple(pins["checkpoints"]),
+                      seed=pins["seed"])
+    assert {str(k): v for k, v in got.items()} == pins["digests"][f"{name}_{g}"]
