@@ -14,6 +14,8 @@ Outputs (committed):
   net_<cfg>.npz     GameNet.forward / GameNet.evaluate outputs of the reference
                     nets on synthetic weights (oracle/synth.py)
   META.json         interpreter / library versions the fixtures were made with
+(make_digests.py and make_mcts_digests.py, run the same way, add digests.json -- 100 000 positions per
+BASELINE game -- and mcts_digests.json -- 512 full reference MCTS games.)
 
 The evaluators and synthetic weights are *inputs* shared with the tests
 (oracle/evaluators.py, oracle/synth.py); every recorded OUTPUT comes from the

@@ -424,3 +424,52 @@ def test_fused_round_stepped_search_matches_oracle(name, g):
             ref.advance(int(actions[t]))
         pool.advance(actions)
     assert pool.counters()["capacity_errors"] == 0
+
+
+@pytest.mark.parametrize("entry_index", range(6))
+def test_full_games_match_reference_mcts_digests(golden_dir, entry_index):
+    """Several hundred full games of the unmodified reference MCTS (tests/golden/make_mcts_digests.py: hashed
+    evaluator, 25 / 50 / 200 simulations per move, subtree reuse, forced random openings), one SHA-256 per
+    game over every move's visit counts, stats, child order, root visits and action.  All games of a plan
+    entry are replayed at once, one tree per game; every digest must match."""
+    import hashlib
+    import random
+    import struct
+    import sys
+    from deep_mcts_b200 import mcts as dm
+    sys.path.insert(0, str(golden_dir))
+    from make_mcts_digests import absorb_move, choose, game_seed
+    pins = json.load(open(golden_dir / "mcts_digests.json"))
+    entry = pins["plan"][entry_index]
+    name, g, sims, T = entry["game"], entry["grid"], entry["sims"], entry["games"]
+    manager = manager_for(name, g)
+    A = manager.num_actions
+    batch = dm.BatchedMCTS(manager, T, sims, None, dm.hashed_state_evaluator(manager, 0))
+    rngs = [random.Random(game_seed(entry_index, k)) for k in range(T)]
+    hashes = [hashlib.sha256() for _ in range(T)]
+    live = np.ones(T, bool)
+    ply = moves = 0
+    while live.any():
+        ids = np.where(live)[0].astype(np.int32)
+        visits, stats = batch.step(tree_ids=ids)
+        order, count, root_visits = batch.pool.root_children()
+        actions = np.full(T, -1, np.int32)
+        for t in ids:
+            v = [int(x) for x in visits[t][:A]]
+            o = [int(a) for a in order[t, : count[t]]]
+            a = choose(rngs[t], ply, t % (pins["max_opening_plies"] + 1), o, v)
+            absorb_move(hashes[t], v, (int(stats[t][0]), int(stats[t][1])), o, int(root_visits[t]), a)
+            actions[t] = a
+            moves += 1
+        batch.advance(actions)
+        _, _, _, fin, outcome = batch.pool.states()
+        for t in ids:
+            if fin[t]:
+                hashes[t].update(struct.pack("<f", float(outcome[t])))
+                live[t] = False
+        ply += 1
+    assert moves == entry["moves"]
+    got = [h.hexdigest() for h in hashes]
+    wrong = [k for k in range(T) if got[k] != entry["digests"][k]]
+    assert not wrong, f"{len(wrong)} of {T} games differ from the reference, first: game {wrong[0]}"
+    assert batch.pool.counters()["capacity_errors"] == 0

@@ -140,3 +140,31 @@ def test_oracle_game_logic_matches_reference_digest_over_100k_positions(golden_d
                       lambda s: (game.is_final(s), game.outcome(s)), max(pins["checkpoints"]), tuple(pins["checkpoints"]),
                       seed=pins["seed"])
     assert {str(k): v for k, v in got.items()} == pins["digests"][f"{name}_{g}"]
+
+
+@pytest.mark.parametrize("entry_index,n_games", [(0, 16), (1, 6), (2, 6), (3, 5), (4, 1), (5, 2)])
+def test_oracle_mcts_matches_reference_game_digests(golden_dir, entry_index, n_games):
+    """The first games of every entry of tests/golden/mcts_digests.json (full games of the unmodified reference
+    MCTS, one SHA-256 per game) replayed by the oracle search.  The GPU suite replays all 512 games."""
+    import hashlib
+    import struct
+    import sys
+    sys.path.insert(0, str(golden_dir))
+    from make_mcts_digests import absorb_move, choose, game_seed
+    pins = json.load(open(golden_dir / "mcts_digests.json"))
+    entry = pins["plan"][entry_index]
+    game = make_game(entry["game"], entry["grid"])
+    for k in range(n_games):
+        rng = random.Random(game_seed(entry_index, k))
+        ref = OracleMCTS(game, entry["sims"], None, oev.hashed)
+        h = hashlib.sha256()
+        ply = 0
+        while not game.is_final(ref.state):
+            _, stats = ref.step()
+            visits, order = ref.root_visit_counts(), ref.root_children_actions()
+            action = choose(rng, ply, k % (pins["max_opening_plies"] + 1), order, visits)
+            absorb_move(h, visits, stats, order, ref.visits[ref.root], action)
+            ref.advance(action)
+            ply += 1
+        h.update(struct.pack("<f", game.outcome(ref.state)))
+        assert h.hexdigest() == entry["digests"][k], (entry["game"], entry["sims"], k)
