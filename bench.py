@@ -148,7 +148,7 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------- clocks
 class ClockSampler:
     QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap,power.draw,power.limit")
 
     def __init__(self, gpu_index):
         self.samples = []
@@ -177,8 +177,19 @@ class ClockSampler:
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(s[2 + i].lower().startswith("active") for s in self.samples)]
+        def floats(col):
+            out = []
+            for s in self.samples:
+                try:
+                    out.append(float(s[col]))
+                except (IndexError, ValueError):
+                    pass
+            return sorted(out)
+        watts, limit = floats(6), floats(7)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm),
+                # board power under load against its limit: the trunk is energy-bound
+                "power_w": watts[len(watts) // 2] if watts else None, "power_limit_w": limit[-1] if limit else None}
 
 
 # --------------------------------------------------------------------------------- b200 arm
