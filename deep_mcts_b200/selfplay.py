@@ -128,8 +128,8 @@ class BatchedSelfPlay:
             current.wait_stream(st)
 
     def _capture_round(self) -> None:
-        """Capture one fused round (memset + tree kernel: expand/backup of the previous batch and the next
-        selection, then the network kernels) into a CUDA graph; the round has no host-visible state, so
+        """Capture one fused round (tree kernel: expand/backup of the previous batch and the next selection into
+        dense leaf slots, then the network kernels) into a CUDA graph; the round has no host-visible state, so
         replaying it is identical to launching it."""
         dn, pool = self.device_nets[0], self.pools[0]
         dn.search_round(pool, selfplay=True, fused=True)        # warm every kernel outside the capture
