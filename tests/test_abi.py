@@ -53,3 +53,18 @@ def test_product_never_imports_oracle():
     for path in (ROOT / "deep_mcts_b200").rglob("*.py"):
         text = path.read_text()
         assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), path
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    """No CPU fallback: if the CUDA library cannot be loaded the product raises, naming the build step."""
+    import importlib
+    from deep_mcts_b200 import _lib
+    monkeypatch.setenv("DM_LIB_PATH", str(tmp_path / "missing.so"))
+    fresh = importlib.reload(_lib)
+    try:
+        with pytest.raises(ImportError) as err:
+            fresh.load()
+        assert "missing.so" in str(err.value) and "no CPU fallback" in str(err.value)
+    finally:
+        monkeypatch.delenv("DM_LIB_PATH")
+        importlib.reload(_lib)
