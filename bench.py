@@ -168,11 +168,20 @@ class ClockSampler:
         for line in self.proc.stdout:
             parts = [p.strip() for p in line.split(",")]
             if len(parts) >= 6:
-                self.samples.append(parts)
+                self.samples.append((time.time(), parts))
+
+    def mark(self):
+        """Start of the timed region: samples taken before it (nvidia-smi is started during the warm-up so
+        that it is already producing lines) are ignored unless nothing arrives inside the region."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is not None:
             self.proc.terminate()
+        t0 = getattr(self, "t0", 0.0)
+        inside = [parts for t, parts in self.samples if t >= t0]
+        # a region shorter than the sampling period may catch no line: fall back to the last warm-up lines
+        self.samples = inside if inside else [parts for _, parts in self.samples[-3:]]
         sm = sorted(int(s[0]) for s in self.samples if s[0].isdigit())
         mx = [int(s[1]) for s in self.samples if s[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -233,16 +242,17 @@ def run_b200(args):
         torch.cuda.synchronize()
 
     # ---- warm-up (also desynchronises the games' phases; captures the round graph when enabled)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
     for _ in range(args.warmup):
         engine.run_rounds(sims)
     barrier()
     c0 = engine.counters()
     launches0 = lib.dm_launch_count() + engine.graph_launches()
-    clocks = ClockSampler(local_rank)
-    if rank == 0:
-        clocks.start()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    clocks.mark()
     start.record()
     for _ in range(args.steps):
         engine.run_rounds(sims)
