@@ -36,8 +36,8 @@ UNIT = "sims/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="othello8", choices=sorted(WORKLOADS))
     ap.add_argument("--trees", type=int, default=4096, help="concurrent games per GPU")
@@ -124,7 +124,8 @@ def run_reference(args):
     from oracle import cpu_selfplay  # noqa: the one place bench.py may execute oracle/
     wl = workload_config(args)
     procs = cpu_selfplay.default_procs()
-    slice_s = 4.0
+    # a "step" of this arm is a bounded slice of CPU self-play; the whole run stays near a minute whatever K + W is
+    slice_s = min(4.0, max(0.5, 60.0 / (args.warmup + args.steps)))
     slices = cpu_selfplay.run(wl, procs, args.warmup + args.steps, slice_s)
     timed = slices[args.warmup:]
     sims = sum(s[0] for s in timed)
@@ -138,7 +139,7 @@ def run_reference(args):
         "config": config_block(args, wl, args.gpus),
         "leaf_evals_per_sec": evals / wall,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port",
-                         "sample": f"{procs} processes x 1 torch thread, {len(timed)} slices of {slice_s:.0f} s "
+                         "sample": f"{procs} processes x 1 torch thread, {len(timed)} slices of {slice_s:.1f} s "
                                    "of full self-play games (oracle port of the reference loop)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
