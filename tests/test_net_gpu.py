@@ -273,3 +273,62 @@ def test_full_batch_is_bitwise_equal_to_small_batches(name, g):
     want_v, want_p = onet.evaluate_batch(game, sd, [states[i] for i in idx])
     np.testing.assert_allclose(p_big[idx], want_p, atol=BF16_ATOL, rtol=0)
     np.testing.assert_allclose(v_big[idx], want_v, atol=BF16_ATOL, rtol=0)
+
+
+@pytest.mark.parametrize("name,g,precision", [("othello", 8, "fp32"), ("hex", 7, "fp32"), ("othello", 8, "bf16"),
+                                              ("hex_with_swap", 7, "bf16")])
+def test_net_guided_search_is_exact_given_the_device_outputs(name, g, precision):
+    """BASELINE board sizes with the full-width net: the batched search (fused tree rounds, the per-game kernel
+    instances, float priors straight from the network kernels) against the oracle search fed with the SAME
+    network outputs, evaluated one state at a time on the device.  Visit counts, stats and child order must be
+    identical -- for the bf16 tensor-core path as well, since a board's result does not depend on its batch."""
+    from deep_mcts_b200 import mcts as dm
+    from deep_mcts_b200.gamenet import cached_state_evaluator
+    from oracle.mcts import OracleMCTS
+    game = make_game(name, g)
+    sd = synthetic_state_dict(game, 128, 3, 128, seed=17, conv_gain=1.0, fc_scale=1.0)
+    from test_net_cpu import build_net
+    net = build_net(name, g, 128, 3, 128)
+    net.load_state_dict(sd)
+    net.precision = precision
+    net.max_batch = 64
+    dn = net.device_net()
+    cache = {}
+
+    def device_outputs(_, state):
+        hit = cache.get(state)
+        if hit is None:
+            v, p = dn.evaluate([state[0]], [state[1]], [state[2]])
+            hit = cache[state] = (float(v[0]), [float(x) for x in p[0][: game.num_actions]])
+        return hit
+
+    T, sims = 6, 40
+    rs = np.random.RandomState(4)
+    openings = []
+    for t in range(T):
+        s = game.initial_state()
+        for _ in range(t):
+            legal = game.legal_list(s)
+            s = game.child(s, legal[rs.randint(len(legal))])
+        openings.append(s)
+    batch = dm.BatchedMCTS(net.manager, T, sims, None, cached_state_evaluator(net))
+    batch.pool.set_root_states(np.array([o[0] for o in openings], np.uint8), np.array([o[1] for o in openings], np.uint64),
+                               np.array([o[2] for o in openings], np.uint64))
+    refs = []
+    for o in openings:
+        r = OracleMCTS(game, sims, None, device_outputs)
+        r.set_root_state(o)
+        refs.append(r)
+    for move in range(3):
+        visits, stats = batch.step()
+        order, count, _ = batch.pool.root_children()
+        actions = np.zeros(T, np.int32)
+        for t, ref in enumerate(refs):
+            _, ref_stats = ref.step()
+            assert [int(v) for v in visits[t]][: game.num_actions] == ref.root_visit_counts(), (t, move)
+            assert tuple(stats[t]) == tuple(ref_stats)
+            assert [int(a) for a in order[t, : count[t]]] == ref.root_children_actions()
+            actions[t] = int(np.argmax(visits[t]))
+            ref.advance(int(actions[t]))
+        batch.advance(actions)
+    assert batch.pool.counters()["capacity_errors"] == 0
