@@ -110,6 +110,13 @@ def test_selfplay_with_device_net_runs_and_labels_consistently():
     engine2.run_rounds(100)
     torch.cuda.synchronize()
     assert engine2.counters()["games"] > 10
+    f2, s2, p2, pi2, z2 = engine2.sample_batch(48)
+    assert pi2.shape == (48, 17) and z2.shape == (48, 1) and f2.shape == (48,)
+    np.testing.assert_allclose(pi2.sum(dim=1).cpu().numpy(), 1.0, atol=1e-5)
+    # sampling restricted to what was complete at a snapshot, minus the slots about to be overwritten
+    snap = engine2.positions_written_per_pool()
+    f3, _, _, pi3, _ = engine2.sample_batch(16, written=snap, skip_oldest=8)
+    assert f3.shape == (16,) and pi3.shape == (16, 17)
 
 
 def test_pipelined_pool_graph_accounting():
