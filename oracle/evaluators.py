@@ -28,12 +28,17 @@ def mix64(x: int) -> int:
 
 
 def uniform(game: Game, state: State) -> Tuple[float, List[float]]:
+    """The evaluator self-play uses before the first weight transfer: value 0.5, equal priors over the
+    legal actions (reference train.py:240-248)."""
     legal = set(game.legal_list(state))
     n = len(legal)
     return 0.5, [1 / n if a in legal else 0.0 for a in range(game.num_actions)]
 
 
 def hashed_salted(salt: int):
+    """Deterministic synthetic evaluator (a test INPUT, not a restatement of reference code): priors and value
+    are a hash of the state, so the reference MCTS, the oracle and the device engine can be fed identical
+    numbers (the device twin is tree.cu hashed_h0 / hashed_weight)."""
     def evaluator(game: Game, state: State) -> Tuple[float, List[float]]:
         player, first, second = state
         h0 = mix64(first ^ mix64(second ^ mix64(player + 0x9E3779B97F4A7C15 * (salt + 1))))

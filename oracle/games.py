@@ -127,6 +127,7 @@ class Game:
         return set_order(self.legal_list(state))
 
     def legal_mask(self, state: State) -> int:
+        """Bit a set <=> action a is legal: the mask of GameNet._mask_illegal_moves (gamenet.py:122-128)."""
         m = 0
         for a in self.legal_list(state):
             m |= 1 << a
@@ -235,6 +236,7 @@ class Game:
 
 
 def make_game(name_or_id, grid_size: Optional[int] = None) -> Game:
+    """Rules object by name or dm_game id (tic-tac-toe is always 3x3, tictactoe/game.py:24-31)."""
     ids = {v: k for k, v in GAME_NAMES.items()}
     gid = ids[name_or_id] if isinstance(name_or_id, str) else int(name_or_id)
     return Game(gid, 3 if gid == TICTACTOE else int(grid_size))

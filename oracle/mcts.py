@@ -51,6 +51,7 @@ class OracleMCTS:
 
     # mcts.py:243-245
     def reset(self) -> None:
+        """Fresh tree on the initial state (MCTS.reset, mcts.py:243-245)."""
         self.visits: List[int] = [0]
         self.value_sum: List[float] = [0.0]
         self.prior: List[float] = [-1.0]
@@ -180,6 +181,7 @@ class OracleMCTS:
         return dist, (with_exp, without_exp)
 
     def root_visit_counts(self) -> List[int]:
+        """Visits of the root's children by action, the numerators of MCTS.step's result (mcts.py:139-147)."""
         first, n = self.first_child[self.root], self.n_children[self.root]
         counts = [0] * self.game.num_actions
         for c in range(first, first + n):
@@ -187,6 +189,7 @@ class OracleMCTS:
         return counts
 
     def root_children_actions(self) -> List[int]:
+        """``list(root.children)``: the children in creation order = set iteration order (mcts.py:200-215)."""
         first, n = self.first_child[self.root], self.n_children[self.root]
         return [self.action[c] for c in range(first, first + n)]
 
