@@ -48,6 +48,8 @@ def parse_args():
     ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
     ap.add_argument("--pool-sizes", type=str, default="", help="comma-separated games per pool (default: even split)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay a captured CUDA graph of the round")
+    ap.add_argument("--cache-log2", type=int, default=22,
+                    help="log2 entries of the device evaluation cache (reference train.py:408-414); 0 = off")
     return ap.parse_args()
 
 
@@ -232,7 +234,8 @@ def run_b200(args):
     sims, T = wl["num_simulations"], args.trees
     engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
                              replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools,
-                             pool_sizes=[int(x) for x in args.pool_sizes.split(",")] if args.pool_sizes else None)
+                             pool_sizes=[int(x) for x in args.pool_sizes.split(",")] if args.pool_sizes else None,
+                             eval_cache_log2=args.cache_log2 if args.cache_log2 > 0 else None)
     engine.use_graph = bool(args.graph)
     dn = net.device_net()   # e2e leg (full-width batches)
     lib = _lib.load()
@@ -407,6 +410,10 @@ def run_b200(args):
                 "timed_in": f"{prof_steps} extra steps launched kernel by kernel right after the timed region "
                             "(CUDA events cannot be timed inside the replayed graph)",
             },
+            "eval_cache": {"log2_entries": args.cache_log2, "hits": d["cache_hits"], "aliases": d["cache_aliases"],
+                           "inserts": d["cache_inserts"], "leaf_evals": d["leaf_evals"],
+                           "served_fraction": (d["cache_hits"] + d["cache_aliases"]) /
+                                              max(1, d["cache_hits"] + d["cache_aliases"] + d["leaf_evals"])},
             "kernel_ms": {**{k: v[0] for k, v in prof.items()}, **tree_ms},
             "tree_roofline": tree_roofline(pd, tree_ms, peaks),
             "tree_stats": {"mean_depth": d["depth_sum"] / max(1, d["simulations"]),

@@ -12,6 +12,8 @@ from pathlib import Path
 DM_MAX_ACTIONS = 65
 DM_MAX_DEPTH = 128
 DM_MAX_LEAVES = 8
+DM_REPLAY_POS_BITS = 38
+DM_REPLAY_GAME_RING = 1 << 18
 
 DM_TICTACTOE, DM_HEX, DM_HEX_SWAP, DM_OTHELLO = 0, 1, 2, 3
 DM_EVAL_NONE, DM_EVAL_UNIFORM, DM_EVAL_HASHED, DM_EVAL_EXTERNAL = 0, 1, 2, 3
@@ -64,6 +66,7 @@ _SIGNATURES = {
     "dm_game_status": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "dm_game_rollout": (c_int, [c_int, c_int, c_int, _P, _P, _P, c_int, c_uint64, _P, _P, _P]),
     "dm_eval_uniform": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "dm_eval_hashed": (c_int, [c_int, c_int, c_int, _P, _P, _P, _P, _P, c_uint64, _P, _P, _P]),
     "dm_pool_create": (c_int, [POINTER(PoolConfig), POINTER(c_void_p)]),
     "dm_pool_destroy": (c_int, [_P]),
     "dm_pool_configure": (c_int, [_P, POINTER(SearchConfig)]),
@@ -77,10 +80,14 @@ _SIGNATURES = {
     "dm_pool_select": (c_int, [_P, _P]),
     "dm_pool_leaf_buffers": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                      POINTER(c_void_p), POINTER(c_void_p)]),
+    "dm_pool_leaf_index": (c_int, [_P, POINTER(c_void_p)]),
+    "dm_pool_cache_enable": (c_int, [_P, c_int, c_int]),
+    "dm_pool_cache_clear": (c_int, [_P, _P]),
     "dm_pool_expand_backup": (c_int, [_P, _P, c_int, _P, c_int, _P]),
     "dm_pool_round": (c_int, [_P, _P, c_int, _P, c_int, c_int, _P]),
     "dm_pool_root_visits": (c_int, [_P, _P, _P, _P]),
     "dm_pool_root_children": (c_int, [_P, _P, _P, _P, _P]),
+    "dm_pool_root_child_stats": (c_int, [_P, _P, _P, _P]),
     "dm_pool_advance": (c_int, [_P, _P, _P]),
     "dm_pool_states": (c_int, [_P, _P, _P, _P, _P, _P, _P]),
     "dm_pool_counters": (c_int, [_P, POINTER(c_uint64)]),
@@ -88,11 +95,13 @@ _SIGNATURES = {
     "dm_selfplay_select": (c_int, [_P, _P]),
     "dm_selfplay_replay": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p)]),
+    "dm_selfplay_games": (c_int, [_P, POINTER(c_void_p)]),
     "dm_net_create": (c_int, [POINTER(NetConfig), POINTER(c_void_p)]),
     "dm_net_destroy": (c_int, [_P]),
     "dm_net_set_tensor": (c_int, [_P, c_char_p, _P, c_int64]),
     "dm_net_finalize": (c_int, [_P, _P]),
     "dm_net_evaluate": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P]),
+    "dm_net_evaluate_indexed": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P]),
     "dm_net_forward": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P, _P]),
     "dm_net_rollout_greedy": (c_int, [_P, c_int, c_int, _P, _P, _P, _P, _P]),
     "dm_net_profile": (c_int, [_P, c_int]),

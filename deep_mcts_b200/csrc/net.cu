@@ -162,8 +162,8 @@ __global__ void k_greedy_step(GameCfg cfg, int n, u64* first, u64* second, u8* p
     atomicAdd(active, 1);
 }
 
-int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u64* first, const u64* second,
-                const u8* player, int mode, float* value_out, float* probs_out, cudaStream_t st) {
+int run_forward(dm_net* net, int precision, int n, const int* count_dev, const int* index, const u64* first,
+                const u64* second, const u8* player, int mode, float* value_out, float* probs_out, cudaStream_t st) {
     const GameCfg& g = net->game;
     const int C = net->cfg.channels, R = net->cfg.num_residual, P0 = g.g * g.g, gp = g.g + 2;
     const int L = 2 * R + 1;
@@ -172,7 +172,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     netk::HeadParams hp{net->pfc_b, net->vfc1_w, net->vfc1_t, net->vfc1_b, net->vfc2_w, net->vfc2_b, net->cfg.hidden};
     if (precision == 0) {
         int pe = prof_begin(net, 0, st);
-        netk::k_encode_conv1<false><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, first, second, player,
+        netk::k_encode_conv1<false><<<enc_blocks, 256, enc_smem, st>>>(g, n, count_dev, index, first, second, player,
                                                                        net->conv1_w, net->conv1_b, C, net->x0, nullptr, 0);
         prof_end(net, pe, st);
         DM_LAUNCH_CHECK();
@@ -194,7 +194,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         constexpr int kB = 4;
         size_t hs = (size_t)kB * P0 * C * sizeof(float) + (size_t)kB * (net->NA2 + net->cfg.hidden) * sizeof(float);
         int ph = prof_begin(net, 2, st);
-        netk::k_heads<float, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, first, second, player, net->x1,
+        netk::k_heads<float, kB><<<(n + kB - 1) / kB, 256, hs, st>>>(g, n, count_dev, index, first, second, player, net->x1,
                                                                     net->pfc_w, C, net->NA2, net->vplane, hp, mode,
                                                                     value_out, probs_out);
         prof_end(net, ph, st);
@@ -208,7 +208,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
     int pe = prof_begin(net, 0, st);
     const int enc3_groups = (n + netk::kEncode3Boards - 1) / netk::kEncode3Boards;
     const int enc3_blocks = std::min(enc3_groups, netk::kEncode3CtasPerSm * net->sm_count);
-    netk::k_encode_conv1_table<<<enc3_blocks, 256, netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, first, second, player,
+    netk::k_encode_conv1_table<<<enc3_blocks, 256, netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, index, first, second, player,
                                                                          net->conv1_tab16, C, net->a0,
                                                                          net->rows_total, net->pair_layout ? 1 : 0);
     prof_end(net, pe, st);
@@ -302,7 +302,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const u
         const int fb = (n + netk::kFinishBoards - 1) / netk::kFinishBoards, ft = netk::kFinishBoards * 32;
         const size_t fs = (size_t)P0 * net->cfg.hidden * sizeof(float);
 #define DM_FINISH(GAME, G)                                                                                             \
-    netk::k_heads_finish<GAME, G><<<fb, ft, fs, st>>>(g, n, count_dev, first, second, player, net->fc_partial,          \
+    netk::k_heads_finish<GAME, G><<<fb, ft, fs, st>>>(g, n, count_dev, index, first, second, player, net->fc_partial,   \
                                                       net->fc_split, n_cap, net->fc_na, net->vplane, hp, mode, value_out, \
                                                       probs_out)
         if (g.game == DM_OTHELLO && g.g == 8) DM_FINISH(DM_OTHELLO, 8);
@@ -542,16 +542,26 @@ extern "C" int dm_net_evaluate(dm_net* net, int precision, int n, const int32_t*
                                void* stream) {
     int rc = check_eval_args(net, precision, n, first, second, player, value, probs);
     if (rc != DM_OK) return rc < 0 ? rc : DM_OK;
-    return run_forward(net, precision, n, count_dev, (const u64*)first, (const u64*)second, player, 0, value, probs,
-                       (cudaStream_t)stream);
+    return run_forward(net, precision, n, count_dev, nullptr, (const u64*)first, (const u64*)second, player, 0, value,
+                       probs, (cudaStream_t)stream);
+}
+
+extern "C" int dm_net_evaluate_indexed(dm_net* net, int precision, int n, const int32_t* count_dev,
+                                       const int32_t* index_dev, const uint64_t* first, const uint64_t* second,
+                                       const uint8_t* player, float* value, float* probs, void* stream) {
+    int rc = check_eval_args(net, precision, n, first, second, player, value, probs);
+    if (rc != DM_OK) return rc < 0 ? rc : DM_OK;
+    DM_CHECK_ARG(count_dev && index_dev, "dm_net_evaluate_indexed: count_dev and index_dev are required");
+    return run_forward(net, precision, n, count_dev, index_dev, (const u64*)first, (const u64*)second, player, 0, value,
+                       probs, (cudaStream_t)stream);
 }
 
 extern "C" int dm_net_forward(dm_net* net, int precision, int n, const uint64_t* first, const uint64_t* second,
                               const uint8_t* player, float* value, float* logits, void* stream) {
     int rc = check_eval_args(net, precision, n, first, second, player, value, logits);
     if (rc != DM_OK) return rc < 0 ? rc : DM_OK;
-    return run_forward(net, precision, n, nullptr, (const u64*)first, (const u64*)second, player, 1, value, logits,
-                       (cudaStream_t)stream);
+    return run_forward(net, precision, n, nullptr, nullptr, (const u64*)first, (const u64*)second, player, 1, value,
+                       logits, (cudaStream_t)stream);
 }
 
 extern "C" int dm_net_rollout_greedy(dm_net* net, int precision, int n, const uint64_t* first,
@@ -564,8 +574,8 @@ extern "C" int dm_net_rollout_greedy(dm_net* net, int precision, int n, const ui
     DM_CUDA(cudaMemcpyAsync(net->r_player, player, (size_t)n, cudaMemcpyDeviceToDevice, st));
     const int max_plies = 2 * net->game.cells + 4;
     for (int ply = 0; ply <= max_plies; ++ply) {
-        rc = run_forward(net, precision, n, nullptr, net->r_first, net->r_second, net->r_player, 0, net->r_value,
-                         net->r_probs, st);
+        rc = run_forward(net, precision, n, nullptr, nullptr, net->r_first, net->r_second, net->r_player, 0,
+                         net->r_value, net->r_probs, st);
         if (rc != DM_OK) return rc;
         DM_CUDA(cudaMemsetAsync(net->r_active, 0, sizeof(int), st));
         k_greedy_step<<<(n + 127) / 128, 128, 0, st>>>(net->game, n, net->r_first, net->r_second, net->r_player,

@@ -411,7 +411,7 @@ __host__ __device__ inline size_t encode3_table_bytes(int C) { return (size_t)kE
 inline size_t encode3_smem_bytes(int C, int g) {
     return encode3_table_bytes(C) + (size_t)kEncode3Boards * (g + 2) * (g + 2) + 64;
 }
-__global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, const int* count_dev,
+__global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, const int* count_dev, const int* index,
                                                             const u64* first, const u64* second, const u8* player,
                                                             const __half* __restrict__ tab16,   // [113][C + 8]
                                                             int C, __nv_bfloat16* out_bf16, size_t rows_total,
@@ -458,9 +458,10 @@ __global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, 
     {
         const int b = (int)blockIdx.x * kEncode3Boards + my_bb;
         if (fills && b < live) {
-            nf = first[b];
-            ns = second[b];
-            npl = player[b];
+            const int src = index ? index[b] : b;   // board b of the batch is state index[b] (compacted dense batch)
+            nf = first[src];
+            ns = second[src];
+            npl = player[src];
         }
     }
     bool tables_ready = false;
@@ -471,9 +472,10 @@ __global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, 
         {   // prefetch the next group's bitboards
             const int b = (grp + (int)gridDim.x) * kEncode3Boards + my_bb;
             if (fills && b < live) {
-                nf = first[b];
-                ns = second[b];
-                npl = player[b];
+                const int src = index ? index[b] : b;
+                nf = first[src];
+                ns = second[src];
+                npl = player[src];
             }
         }
         __syncthreads();   // the previous group's codes are no longer read
@@ -1293,7 +1295,8 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_policy_fc_tc(FcArgs args) {
 constexpr int kFinishBoards = 16;
 // GAME >= 0: instantiated for one (game, board size), so the legality mask's bitboard code has constant shifts.
 template <int GAME, int G>
-__global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg_in, int n, const int* count_dev, const u64* first,
+__global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg_in, int n, const int* count_dev, const int* index,
+                                                      const u64* first,
                                                       const u64* second, const u8* player,
                                                       const float* __restrict__ partial, int split, int n_cap, int NA,
                                                       const float* __restrict__ vplane, HeadParams hp, int mode,
@@ -1315,10 +1318,11 @@ __global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg
     }
     __syncthreads();
     if (gb >= live) return;
+    const int ob = index ? index[gb] : gb;   // the leaf's own slot: where its state is read and its result written
     GState s;
-    s.first = first[gb];
-    s.second = second[gb];
-    s.player = player[gb];
+    s.first = first[ob];
+    s.second = second[ob];
+    s.player = player[ob];
     for (int p = lane; p < P0; p += 32) s_vp[warp][p] = vplane[(size_t)gb * P0 + p];
     __syncwarp();
     float v = 0.f;
@@ -1361,15 +1365,15 @@ __global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg
         lg[na] = acc + hp.pfc_b[src];
     }
     if (mode == 1) {
-        if (lane == 0) value_out[gb] = v;
+        if (lane == 0) value_out[ob] = v;
         na = 0;
         for (int a = lane; a < DM_MAX_ACTIONS; a += 32, ++na)
-            probs_out[(size_t)gb * DM_MAX_ACTIONS + a] = a < A ? lg[na] : 0.f;
+            probs_out[(size_t)ob * DM_MAX_ACTIONS + a] = a < A ? lg[na] : 0.f;
         return;
     }
     float tv = tanhf(v);
     if (s.player == 1) tv = -tv;
-    if (lane == 0) value_out[gb] = (tv + 1.f) / 2.f;
+    if (lane == 0) value_out[ob] = (tv + 1.f) / 2.f;
     float mx = -INFINITY;
     na = 0;
     for (int a = lane; a < A; a += 32, ++na) mx = fmaxf(mx, lg[na]);
@@ -1396,7 +1400,7 @@ __global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg
     for (int off = 16; off > 0; off >>= 1) msum += __shfl_xor_sync(DM_FULL_MASK, msum, off);
     na = 0;
     for (int a = lane; a < DM_MAX_ACTIONS; a += 32, ++na)
-        probs_out[(size_t)gb * DM_MAX_ACTIONS + a] = a < A ? e[na] / msum : 0.f;
+        probs_out[(size_t)ob * DM_MAX_ACTIONS + a] = a < A ? e[na] / msum : 0.f;
 }
 
 }  // namespace netk

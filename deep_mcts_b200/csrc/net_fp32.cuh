@@ -45,7 +45,8 @@ __device__ __forceinline__ void write_planes(const GameCfg& cfg, u64 first, u64 
 // kBf16 = false: out_f32[b][pos][C] (NHWC).  kBf16 = true: padded flat rows, channel chunks of
 // 8: out_bf16[(kc*rows_total + row)*8 + j] (see RowGeom).
 template <bool kBf16>
-__global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const int* count_dev, const u64* first,
+__global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const int* count_dev, const int* index,
+                                                      const u64* first,
                                                       const u64* second, const u8* player, const float* __restrict__ w,
                                                       const float* __restrict__ bias, int C, float* out_f32,
                                                       __nv_bfloat16* out_bf16, size_t rows_total) {
@@ -61,8 +62,10 @@ __global__ void __launch_bounds__(256) k_encode_conv1(GameCfg cfg, int n, const 
     for (int i = threadIdx.x; i < C; i += blockDim.x) s_b[i] = bias[i];
     for (int bb = 0; bb < kEncodeBoards; ++bb) {
         int b = b0 + bb;
-        if (b < live)
-            write_planes(cfg, first[b], second[b], player[b], s_planes + bb * 3 * gp * gp, threadIdx.x, blockDim.x);
+        if (b < live) {
+            const int src = index ? index[b] : b;   // board b of the batch is state index[b] (compacted dense batch)
+            write_planes(cfg, first[src], second[src], player[src], s_planes + bb * 3 * gp * gp, threadIdx.x, blockDim.x);
+        }
     }
     __syncthreads();
     const RowGeom geom = RowGeom::make(g);
@@ -213,7 +216,8 @@ struct HeadParams {
 // mode 0: evaluate -> value in [0,1], probs masked + renormalised; mode 1: raw value, logits.
 // One block = kBoards boards; threads split (action pair, K slice).
 template <typename T, int kBoards>
-__global__ void __launch_bounds__(256) k_heads(GameCfg cfg, int n, const int* count_dev, const u64* first,
+__global__ void __launch_bounds__(256) k_heads(GameCfg cfg, int n, const int* count_dev, const int* index,
+                                               const u64* first,
                                                const u64* second, const u8* player, const T* __restrict__ t_act,
                                                const T* __restrict__ pfc_w, int C, int NA2,
                                                const float* __restrict__ vplane, HeadParams hp, int mode,
@@ -283,6 +287,7 @@ __global__ void __launch_bounds__(256) k_heads(GameCfg cfg, int n, const int* co
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int b = warp; b < nb; b += nwarps) {
         int gb = b0 + b;
+        if (index) gb = index[gb];   // states are read and results written at the leaf's own slot
         GState s;
         s.first = first[gb];
         s.second = second[gb];

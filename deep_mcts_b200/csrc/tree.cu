@@ -24,13 +24,24 @@ namespace {
 constexpr int kWarpsPerBlock = 4;
 constexpr u8 kFlagNeedNoise = 1;
 constexpr u8 kFlagStepActive = 2;
-constexpr u8 kLeafRoot = 1;  // leaf is a root expansion: only root.visits += 1 (mcts.py:114-116)
+constexpr u8 kLeafRoot = 1;    // leaf is a root expansion: only root.visits += 1 (mcts.py:114-116)
+constexpr u8 kLeafAlias = 2;   // evaluation cache: another tree's leaf of the same round is the same state; its slot holds the result
+constexpr u8 kLeafCached = 4;  // evaluation cache: the result was copied from the table into the tree's hit row
 
 enum Counter {
     kCntSims = 0, kCntLeafEvals = 1, kCntTerminal = 2, kCntNodesHigh = 3, kCntGames = 4, kCntDepth = 5,
     kCntScanned = 6, kCntCreated = 7, kCntCapacity = 8, kCntMoves = 9, kCntRolloutPlies = 10, kCntInvalid = 11,
-    kCntCompactions = 12
+    kCntCompactions = 12, kCntCacheHits = 13, kCntCacheAliases = 14, kCntCacheInserts = 15
 };
+
+// ---- evaluation cache (cached_state_evaluator, train.py:408-414) ---------------------------
+// Open-addressing table in HBM keyed by the 17-byte state; a row is the evaluator's output for that
+// state (priors by action, then the value).  ctl word: status[63:62] player[61] stamp[60:32] slot[31:0].
+constexpr int kCacheWays = 8;           // consecutive entries probed by lanes 0..7
+constexpr int kCacheRow = 68;           // DM_MAX_ACTIONS priors + value + 2 pad (16-byte multiple)
+constexpr u64 kCtlEmpty = 0, kCtlLocked = 1, kCtlPending = 2, kCtlValid = 3;
+constexpr u32 kStampMask = 0x1fffffffu;
+constexpr int kCacheMiss = 0, kCacheHit = 1, kCacheAlias = 2;
 
 struct PoolView {
     GameCfg cfg;
@@ -90,6 +101,19 @@ struct PoolView {
     u32* cprefix;   // [n_trees][cap_words]
     u32 cap_words;
     unsigned long long* counters;
+    // evaluation cache (cctl == null: disabled)
+    unsigned long long* cctl;   // [centries]
+    u64* ckey_first;            // [centries]
+    u64* ckey_second;           // [centries]
+    void* crow;                 // [centries][kCacheRow] float or double (cache_f64)
+    void* hit_row;              // [n_trees][kCacheRow] row copied out of the table for a pending cache hit
+    u32 cmask;                  // centries - 1
+    int cache_f64;
+    u32* cround;                // [0] search-round stamp, [1] blocks finished in the running launch
+    int* pend_centry;           // [n_trees] entry claimed for the pending leaf (-1: none)
+    unsigned long long* pend_cctl;  // [n_trees] the pending ctl word that claim published
+    u8* leaf_live;              // [n_trees] dense mode: 1 = slot t holds a leaf the evaluator must run
+    int* leaf_index;            // [n_trees] dense mode: compacted list of the live slots (count in leaf_count)
     // self-play recording
     int selfplay;
     u64* ex_first;  // [n_trees][DM_MAX_DEPTH]
@@ -102,7 +126,8 @@ struct PoolView {
     u8* rp_player;
     float* rp_pi;
     float* rp_z;
-    unsigned long long* rp_written;
+    unsigned long long* rp_written;   // positions written (low DM_REPLAY_POS_BITS bits) | games written (high bits)
+    unsigned long long* rp_game_end;  // [DM_REPLAY_GAME_RING] positions written up to and including game i
 };
 
 // ------------------------------------------------------------------ small warp helpers
@@ -154,6 +179,177 @@ __device__ __forceinline__ u64 hashed_h0(const GState& s, u64 salt) {
 }
 __device__ __forceinline__ u32 hashed_weight(u64 h0, int a) {
     return (u32)((mix64(h0 + (u64)a * 0xD6E8FEB86659FD93ull) >> 40) % 997ull) + 1u;
+}
+
+
+// ---- evaluation cache: device side ---------------------------------------------------------
+// Result-transparent memo of the external evaluator (cached_state_evaluator, train.py:408-414) plus
+// de-duplication of equal leaves inside one round.  Protocol (one search round = one launch of a
+// selecting kernel; `now` is the round stamp, bumped by the last block of that launch):
+//   select:  probe kCacheWays consecutive entries.
+//            valid entry with the leaf's key   -> HIT: the row is copied to the tree's hit row now (rows of
+//                                                 valid entries are never written during a launch) and the
+//                                                 leaf needs no evaluation;
+//            pending entry stamped `now`       -> ALIAS: another tree hands the same state to the evaluator
+//                                                 in this round; remember its slot;
+//            otherwise                         -> MISS: lock a victim entry (CAS), write the key, publish
+//                                                 pending(now, slot); the leaf is evaluated.
+//   expand:  the tree that published an entry copies the evaluator's output into the row and flips the
+//            entry to valid (only if the ctl word is still the one it published).
+// A key is matched seqlock-style (ctl, key, ctl again), rows are written only while their entry is pending
+// and read only while it is valid, so a reader never sees a torn key or row; everything else (lost
+// claims, replaced entries) only costs a missed hit.  Control words and keys are read through L2.
+__device__ __forceinline__ u64 ctl_make(u64 status, int player, u32 stamp, u32 slot) {
+    return (status << 62) | ((u64)(player & 1) << 61) | ((u64)(stamp & kStampMask) << 32) | (u64)slot;
+}
+__device__ __forceinline__ u64 ld_ctl(const unsigned long long* p) { return __ldcv(p); }
+
+struct CacheProbe {
+    int kind;    // kCacheMiss / kCacheHit / kCacheAlias
+    int entry;   // hit: matching entry; miss: locked victim entry (caller must publish) or -1
+    int slot;    // alias: evaluator slot that will hold the result
+};
+
+__device__ __forceinline__ CacheProbe cache_probe(const PoolView& P, const GState& s, int lane, u32 now) {
+    CacheProbe r;
+    r.kind = kCacheMiss;
+    r.entry = -1;
+    r.slot = -1;
+    const u64 h = mix64(s.first ^ mix64(s.second + 0x9E3779B97F4A7C15ull * (u64)(s.player + 1)));
+    const u32 idx = ((u32)(h >> 17) + (u32)lane) & P.cmask;
+    const bool prober = lane < kCacheWays;
+    for (int attempt = 0; attempt < 16; ++attempt) {
+        u64 c = 0;
+        u32 st = (u32)kCtlLocked;
+        bool match = false;
+        if (prober) {
+            c = ld_ctl(P.cctl + idx);
+            st = (u32)(c >> 62);
+            if (st >= (u32)kCtlPending && (int)((c >> 61) & 1) == s.player) {
+                const u64 kf = __ldcv(P.ckey_first + idx), ks = __ldcv(P.ckey_second + idx);
+                __threadfence();
+                match = kf == s.first && ks == s.second && ld_ctl(P.cctl + idx) == c;
+            }
+        }
+        const u32 mm = __ballot_sync(DM_FULL_MASK, match);
+        if (mm) {
+            const int src = __ffs(mm) - 1;
+            const u64 cm = __shfl_sync(DM_FULL_MASK, c, src);
+            const u32 e = __shfl_sync(DM_FULL_MASK, idx, src);
+            if ((cm >> 62) == kCtlValid) {
+                r.kind = kCacheHit;
+                r.entry = (int)e;
+                return r;
+            }
+            if ((u32)((cm >> 32) & kStampMask) == (now & kStampMask)) {
+                r.kind = kCacheAlias;
+                r.slot = (int)(u32)cm;
+                return r;
+            }
+            // a pending entry of an earlier round: its result is in flight or lost -- evaluate again, do not insert
+            return r;
+        }
+        const u32 locked = __ballot_sync(DM_FULL_MASK, prober && st == (u32)kCtlLocked);
+        if (locked && attempt < 12) {   // somebody is publishing in this window, possibly this very key
+            __nanosleep(40);
+            continue;
+        }
+        // victim: empty, else a pending entry nobody will complete, else the oldest valid entry; entries of
+        // this and the previous round (live owners) last
+        u32 score = 0xffffffffu;
+        if (prober && st != (u32)kCtlLocked) {
+            const u32 age = (now - (u32)((c >> 32) & kStampMask)) & kStampMask;
+            if (st == (u32)kCtlEmpty) score = 0;
+            else if (st == (u32)kCtlPending) score = age >= 2 ? 1u : 0xfffffff0u + age;
+            else score = 2u + (kStampMask - age);
+        }
+        const u32 best = __reduce_min_sync(DM_FULL_MASK, score);
+        if (best == 0xffffffffu) return r;
+        const int src = __ffs(__ballot_sync(DM_FULL_MASK, score == best)) - 1;
+        const u32 e = __shfl_sync(DM_FULL_MASK, idx, src);
+        const u64 cv = __shfl_sync(DM_FULL_MASK, c, src);
+        int ok = 0;
+        if (lane == 0) ok = atomicCAS(P.cctl + e, cv, ctl_make(kCtlLocked, 0, 0, 0)) == cv;
+        ok = __shfl_sync(DM_FULL_MASK, ok, 0);
+        if (ok) {
+            r.entry = (int)e;
+            return r;
+        }
+    }
+    return r;
+}
+
+// after a successful lock: write the key and publish pending(now, slot)   (lane 0)
+__device__ __forceinline__ void cache_publish(const PoolView& P, int t, int entry, const GState& s, u32 now, int slot) {
+    P.ckey_first[entry] = s.first;
+    P.ckey_second[entry] = s.second;
+    __threadfence();
+    const u64 c = ctl_make(kCtlPending, s.player, now, (u32)slot);
+    atomicExch(P.cctl + entry, c);
+    P.pend_centry[t] = entry;
+    P.pend_cctl[t] = c;
+}
+
+// copy the row of a (validated) hit into the tree's hit row; whole warp
+template <typename PriorT>
+__device__ __forceinline__ void cache_copy_hit(const PoolView& P, int t, int entry, int lane) {
+    const PriorT* row = (const PriorT*)P.crow + (size_t)entry * kCacheRow;
+    PriorT* dst = (PriorT*)P.hit_row + (size_t)t * kCacheRow;
+    for (int j = lane; j < DM_MAX_ACTIONS + 1; j += 32) dst[j] = __ldcg(row + j);
+    __syncwarp();
+}
+
+// the owner of a pending entry stores the evaluator's output; whole warp
+template <typename PriorT>
+__device__ __forceinline__ void cache_finalize(const PoolView& P, int t, int lane, const PriorT* pr, PriorT value) {
+    const int e = P.pend_centry[t];
+    if (e < 0) return;
+    const u64 expect = P.pend_cctl[t];
+    if (ld_ctl(P.cctl + e) == expect) {
+        PriorT* row = (PriorT*)P.crow + (size_t)e * kCacheRow;
+        for (int j = lane; j < P.cfg.num_actions; j += 32) row[j] = pr[j];
+        if (lane == 0) row[DM_MAX_ACTIONS] = value;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) {
+            atomicCAS(P.cctl + e, expect, (expect & ~(3ull << 62)) | (kCtlValid << 62));
+            count(P, kCntCacheInserts, 1);
+        }
+    }
+    if (lane == 0) P.pend_centry[t] = -1;
+    __syncwarp();
+}
+
+// End of a selecting launch.  The last block to finish bumps the round stamp and, in dense mode, compacts the
+// live leaf slots into leaf_index / leaf_count for the evaluator (ascending tree order, deterministic).
+__device__ __forceinline__ void round_end(const PoolView& P, bool dense) {
+    __shared__ u32 s_last;
+    __shared__ u32 s_warp_sums[kWarpsPerBlock];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = atomicInc(P.cround + 1, gridDim.x - 1) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) P.cround[0] = (P.cround[0] + 1) & kStampMask;
+    if (!dense) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = kWarpsPerBlock * 32;
+    u32 running = 0;
+    for (int base = 0; base < P.n_trees; base += nthreads) {
+        const int t = base + (int)threadIdx.x;
+        const bool live = t < P.n_trees && __ldcv(P.leaf_live + t) != 0;
+        const u32 bal = __ballot_sync(DM_FULL_MASK, live);
+        if (lane == 0) s_warp_sums[warp] = __popc(bal);
+        __syncthreads();
+        u32 before = running;
+        for (int w = 0; w < warp; ++w) before += s_warp_sums[w];
+        if (live) P.leaf_index[before + __popc(bal & ((1u << lane) - 1u))] = t;
+        for (int w = 0; w < kWarpsPerBlock; ++w) running += s_warp_sums[w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *P.leaf_count = (int)running;
 }
 
 // ------------------------------------------------------------------------------ select
@@ -298,7 +494,7 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
         int a = s_order[j];
         double p;
         if (eval_kind == DM_EVAL_HASHED) p = __ddiv_rn((double)hashed_weight(h0, a), total);
-        else if (eval_kind == DM_EVAL_EXTERNAL) p = ext_f64 ? ext_f64[a] : (double)ext_f32[a];
+        else if (eval_kind == DM_EVAL_EXTERNAL) p = ext_f64 ? __ldcg(ext_f64 + a) : (double)__ldcg(ext_f32 + a);
         else p = uniform_p;
         P.visits[c] = 0;
         P.value_sum[c] = 0.0;
@@ -686,6 +882,17 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
     u32 first = P.first_child[base + root];
     GState s = root_state(P, t);
     u32 ply = P.ply[t];
+    if (n == 0) {
+        // the root was never expanded (its expansion hit the arena's capacity, already counted): there is no
+        // move to choose.  Abandon the game without recording it and start over instead of re-rooting on garbage.
+        if (lane == 0) {
+            fresh_root(P, t, game_initial(P.cfg));
+            P.ply[t] = 0;
+            arm_step(P, t);
+        }
+        __syncwarp();
+        return;
+    }
     // visit totals
     u32 v[3] = {0, 0, 0};
     int a[3] = {0, 0, 0};
@@ -770,9 +977,12 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
     if (final) {
         // label every recorded position with the outcome from its mover's perspective
         u32 cnt = min(ply, (u32)DM_MAX_DEPTH);
-        unsigned long long slot0 = 0;
-        if (lane == 0) slot0 = atomicAdd(P.rp_written, (unsigned long long)cnt);
-        slot0 = __shfl_sync(DM_FULL_MASK, slot0, 0);
+        // one atomic hands out the game's positions AND its game number, so games are numbered in ring order
+        unsigned long long packed = 0;
+        if (lane == 0) packed = atomicAdd(P.rp_written, (1ull << DM_REPLAY_POS_BITS) | (unsigned long long)cnt);
+        packed = __shfl_sync(DM_FULL_MASK, packed, 0);
+        const unsigned long long slot0 = packed & ((1ull << DM_REPLAY_POS_BITS) - 1ull);
+        if (lane == 0) P.rp_game_end[(packed >> DM_REPLAY_POS_BITS) & (DM_REPLAY_GAME_RING - 1)] = slot0 + cnt;
         float z = outcome * 2.0f - 1.0f;  // train.py:270-272
         for (u32 i = 0; i < cnt; ++i) {
             size_t e = (size_t)t * DM_MAX_DEPTH + i;
@@ -816,7 +1026,7 @@ constexpr int kLevelBudget = 32;
 // self-play keeps every tree busy, so nothing is wasted and the per-leaf atomicAdd on ONE counter
 // -- 4096 returning atomics on the same address, ~13 % of the kernel's stall samples -- goes away.
 template <bool kSelfPlay, bool kDense = false>
-__device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, u32* path) {
+__device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, u32* path, u32 now) {
     const size_t base = (size_t)t * P.cap;
     unsigned long long scanned = 0, depth = 0, terminal = 0, done = 0;
     if (kSelfPlay) {
@@ -831,7 +1041,7 @@ __device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, 
     int sims = P.sims_left[t];
     u8 flags = P.flags[t];
     u32 without = P.stat_without[t];
-    bool emitted = false;
+    bool emitted = false, live = false;
     int levels = 0;
     while (sims > 0) {
         u32 root = P.root[t];
@@ -874,20 +1084,44 @@ __device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, 
                 continue;
             }
         }
-        // hand the leaf to the evaluator
+        // hand the leaf to the evaluator -- unless the evaluation cache already knows the state (hit) or another
+        // tree hands the same state out in this very round (alias)
         int slot = t;
-        if (!kDense) {
+        int centry = -1;
+        if (P.cctl) {
+            const CacheProbe probe = cache_probe(P, s, lane, now);
+            if (probe.kind == kCacheHit) {
+                if (P.cache_f64) cache_copy_hit<double>(P, t, probe.entry, lane);
+                else cache_copy_hit<float>(P, t, probe.entry, lane);
+                leaf_flag |= kLeafCached;
+                live = false;
+            } else if (probe.kind == kCacheAlias) {
+                slot = probe.slot;
+                leaf_flag |= kLeafAlias;
+                live = false;
+            } else {
+                centry = probe.entry;
+                live = true;
+            }
+        } else {
+            live = true;
+        }
+        if (live && !kDense) {
             if (lane == 0) slot = atomicAdd(P.leaf_count, 1);
             slot = __shfl_sync(DM_FULL_MASK, slot, 0);
         }
         for (int i = lane; i < len; i += 32) P.path[(size_t)t * DM_MAX_DEPTH + i] = path[i];
         if (lane == 0) {
+            if (centry >= 0) cache_publish(P, t, centry, s, now, slot);
+            else if (P.cctl) P.pend_centry[t] = -1;
             P.path_len[t] = len;
-            P.leaf_first[slot] = s.first;
-            P.leaf_second[slot] = s.second;
-            P.leaf_player[slot] = (u8)s.player;
-            P.leaf_flags[slot] = leaf_flag;
-            P.leaf_tree[slot] = t;
+            if (live) {
+                P.leaf_first[slot] = s.first;
+                P.leaf_second[slot] = s.second;
+                P.leaf_player[slot] = (u8)s.player;
+                P.leaf_flags[slot] = leaf_flag;
+                P.leaf_tree[slot] = t;
+            }
             P.pend_slot[t] = slot;
             P.pend_first[t] = s.first;
             P.pend_second[t] = s.second;
@@ -901,6 +1135,7 @@ __device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, 
         P.sims_left[t] = sims;
         P.stat_without[t] = without;
         P.flags[t] = flags;
+        if (kDense) P.leaf_live[t] = live ? 1 : 0;
         if (!emitted) P.path_len[t] = 0;
         count(P, kCntSims, done);
         count(P, kCntTerminal, terminal);
@@ -914,8 +1149,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
     __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= P.n_trees) return;
-    select_tree<kSelfPlay>(P, t, lane, s_path[warp]);
+    const u32 now = __ldcv(P.cround);
+    if (t < P.n_trees) select_tree<kSelfPlay>(P, t, lane, s_path[warp], now);
+    round_end(P, false);
 }
 
 // expand_node + rollout mix + backpropagate for one pending leaf (state s, evaluator output in slot `slot`)
@@ -927,7 +1163,11 @@ __device__ __forceinline__ void expand_backup_tree(const PoolView& P, int t, int
     const int len = P.path_len[t];
     const u32* path = P.path + (size_t)t * DM_MAX_DEPTH;
     double ev;
-    const PriorT* pr = priors + (size_t)slot * stride;
+    // evaluator output for this leaf: the tree's own slot, the slot of the tree it aliased in the same round, or
+    // the row the selection copied out of the evaluation cache
+    const bool cached = (leaf_flag & kLeafCached) != 0, alias = (leaf_flag & kLeafAlias) != 0;
+    const PriorT* pr = cached ? (const PriorT*)P.hit_row + (size_t)t * kCacheRow : priors + (size_t)slot * stride;
+    const PriorT leaf_value = cached ? pr[DM_MAX_ACTIONS] : values[slot];
     bool ok;
     if (sizeof(PriorT) == 8) ok = expand(P, t, lane, path[len - 1], s, order, DM_EVAL_EXTERNAL, nullptr, (const double*)pr, ev);
     else ok = expand(P, t, lane, path[len - 1], s, order, DM_EVAL_EXTERNAL, (const float*)pr, nullptr, ev);
@@ -935,10 +1175,12 @@ __device__ __forceinline__ void expand_backup_tree(const PoolView& P, int t, int
         if (lane == 0) {
             P.sims_left[t] = 0;
             P.path_len[t] = 0;
+            if (P.cctl) P.pend_centry[t] = -1;
         }
         __syncwarp();
         return;
     }
+    if (P.cctl && !cached && !alias) cache_finalize<PriorT>(P, t, lane, pr, leaf_value);
     unsigned long long plies = 0;
     if (leaf_flag & kLeafRoot) {
         if (lane == 0) P.visits[base + path[0]] += 1;  // root.visits += 1, value unused
@@ -949,7 +1191,7 @@ __device__ __forceinline__ void expand_backup_tree(const PoolView& P, int t, int
             if (lane == 0) P.flags[t] = flags & ~kFlagNeedNoise;
         }
     } else {
-        double value = (double)values[slot];
+        double value = (double)leaf_value;
         if (P.rollout_kind != DM_ROLLOUT_NONE) {
             Philox rng;
             rng.init(P.seed, (u32)t, 0x73696d00u, P.rng_ctr[t]);
@@ -965,7 +1207,7 @@ __device__ __forceinline__ void expand_backup_tree(const PoolView& P, int t, int
     }
     if (lane == 0) {
         P.path_len[t] = 0;
-        count(P, kCntLeafEvals, 1);
+        count(P, cached ? kCntCacheHits : (alias ? kCntCacheAliases : kCntLeafEvals), 1);
         count(P, kCntRolloutPlies, plies);
     }
     __syncwarp();
@@ -976,15 +1218,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     k_expand_backup(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
     __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int slot = blockIdx.x * kWarpsPerBlock + warp;
-    if (slot >= *P.leaf_count) return;
-    int t = P.leaf_tree[slot];
-    if (P.path_len[t] <= 0) return;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees || P.path_len[t] <= 0) return;
+    // the per-tree copy of the pending leaf: a leaf served by the evaluation cache or aliased to another tree's
+    // slot has no slot of its own in the batch
     GState s;
-    s.first = P.leaf_first[slot];
-    s.second = P.leaf_second[slot];
-    s.player = P.leaf_player[slot];
-    expand_backup_tree<PriorT>(P, t, slot, lane, s, P.leaf_flags[slot], s_order[warp], priors, stride, values);
+    s.first = P.pend_first[t];
+    s.second = P.pend_second[t];
+    s.player = P.pend_player[t];
+    expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
 }
 
 // One launch per search round: expand + back up the tree's pending leaf with the evaluator's output,
@@ -1002,16 +1244,18 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
     if (GAME >= 0) P.cfg = const_game_cfg<(GAME >= 0 ? GAME : 0), (G > 0 ? G : 8)>();
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= P.n_trees) return;
-    if (P.path_len[t] > 0) {
-        GState s;
-        s.first = P.pend_first[t];
-        s.second = P.pend_second[t];
-        s.player = P.pend_player[t];
-        expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
+    const u32 now = __ldcv(P.cround);
+    if (t < P.n_trees) {
+        if (P.path_len[t] > 0) {
+            GState s;
+            s.first = P.pend_first[t];
+            s.second = P.pend_second[t];
+            s.player = P.pend_player[t];
+            expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
+        }
+        select_tree<kSelfPlay, kSelfPlay>(P, t, lane, s_path[warp], now);
     }
-    if (kSelfPlay && blockIdx.x == 0 && threadIdx.x == 0) *P.leaf_count = P.n_trees;   // dense leaf batch
-    select_tree<kSelfPlay, kSelfPlay>(P, t, lane, s_path[warp]);
+    round_end(P, kSelfPlay);   // dense leaf batch (self-play): the last block compacts the live slots
 }
 
 template <bool kSelfPlay, typename PriorT>
@@ -1196,6 +1440,33 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     }
 }
 
+// the DM_EVAL_HASHED evaluator as an EXTERNAL one (double outputs): lets the parity tests drive the
+// leaf-exchange kernels, the dense/compacted leaf batch and the evaluation cache with an evaluator whose
+// reference results are pinned (tests/golden/mcts_digests.json)
+__global__ void k_eval_hashed(GameCfg cfg, int n, const int* count_dev, const int* index, const u64* first,
+                              const u64* second, const u8* player, u64 salt, double* value, double* probs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int live = count_dev ? min(*count_dev, n) : n;
+    if (i >= live) return;
+    const int src = index ? index[i] : i;
+    GState s;
+    s.first = first[src];
+    s.second = second[src];
+    s.player = player[src];
+    bool extra;
+    const u64 m = game_legal_mask(cfg, s, extra);
+    const u64 h0 = hashed_h0(s, salt);
+    u32 sum = 0;
+    for (int a = 0; a < cfg.num_actions; ++a)
+        if (a < cfg.cells ? ((m >> a) & 1) : extra) sum += hashed_weight(h0, a);
+    double* row = probs + (size_t)src * DM_MAX_ACTIONS;
+    for (int a = 0; a < DM_MAX_ACTIONS; ++a) {
+        const bool legal = a < cfg.cells ? ((m >> a) & 1) : (a == cfg.cells && extra);
+        row[a] = legal ? __ddiv_rn((double)hashed_weight(h0, a), (double)sum) : 0.0;
+    }
+    value[src] = __ddiv_rn((double)((h0 >> 20) % 1001ull), 1000.0);
+}
+
 // ------------------------------------------------------------------- kernels: read-out
 __global__ void k_root_visits(PoolView P, u32* visits_out, u32* stats_out) {
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -1231,6 +1502,21 @@ __global__ void k_root_children(PoolView P, u8* order_out, int* count_out, u32* 
     if (lane == 0) {
         if (count_out) count_out[t] = n;
         if (root_visits_out) root_visits_out[t] = P.visits[base + root];
+    }
+}
+
+// Node.probability and Node.value_sum of the root's children, in child (dict) order
+__global__ void k_root_child_stats(PoolView P, double* prior_out, double* value_sum_out) {
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int t = blockIdx.x * kWarpsPerBlock + warp;
+    if (t >= P.n_trees) return;
+    const size_t base = (size_t)t * P.cap;
+    u32 root = P.root[t];
+    int n = P.n_children[base + root];
+    u32 first = P.first_child[base + root];
+    for (int j = lane; j < DM_MAX_ACTIONS; j += 32) {
+        if (prior_out) prior_out[(size_t)t * DM_MAX_ACTIONS + j] = j < n ? P.prior[base + first + j] : 0.0;
+        if (value_sum_out) value_sum_out[(size_t)t * DM_MAX_ACTIONS + j] = j < n ? P.value_sum[base + first + j] : 0.0;
     }
 }
 
@@ -1300,6 +1586,7 @@ struct dm_pool {
     dm_pool_config cfg;
     std::vector<void*> allocations;
     bool configured;
+    uint64_t capacity_errors_reported = 0;
 };
 
 namespace {
@@ -1369,7 +1656,9 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
         (rc = pool_alloc(p, &v.pend_flags, T)) ||
         (rc = pool_alloc(p, &v.vl_len, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.vl_slot, T * DM_MAX_LEAVES)) ||
         (rc = pool_alloc(p, &v.vl_count, T)) || (rc = pool_alloc(p, &v.armed, 1)) ||
-        (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)))
+        (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)) ||
+        (rc = pool_alloc(p, &v.cround, 2)) || (rc = pool_alloc(p, &v.leaf_live, T)) ||
+        (rc = pool_alloc(p, &v.leaf_index, T)))
         return fail(rc);
     if (cfg->compaction) {
         v.cap_words = (v.cap + 31) / 32;
@@ -1528,6 +1817,64 @@ extern "C" int dm_pool_select(dm_pool* p, void* stream) {
     return launch_select(p, stream, false);
 }
 
+extern "C" int dm_pool_cache_enable(dm_pool* p, int log2_entries, int is_f64) {
+    DM_CHECK_ARG(p, "dm_pool_cache_enable: null pool");
+    DM_CHECK_ARG(log2_entries >= 10 && log2_entries <= 28, "dm_pool_cache_enable: log2_entries out of range [10, 28]");
+    PoolView& v = p->v;
+    if (v.cctl) {
+        DM_CHECK_ARG(v.cmask == (1u << log2_entries) - 1u && v.cache_f64 == (is_f64 ? 1 : 0),
+                     "dm_pool_cache_enable: the cache already exists with another size or type");
+        return DM_OK;
+    }
+    DM_CUDA(cudaSetDevice(p->cfg.device));
+    DM_CUDA(cudaDeviceSynchronize());
+    const size_t E = (size_t)1 << log2_entries, T = (size_t)v.n_trees, elem = is_f64 ? 8 : 4;
+    unsigned long long* ctl = nullptr;
+    char *rows = nullptr, *hits = nullptr;
+    DM_TRY(pool_alloc(p, &ctl, E));
+    DM_TRY(pool_alloc(p, &v.ckey_first, E, false));
+    DM_TRY(pool_alloc(p, &v.ckey_second, E, false));
+    DM_TRY(pool_alloc(p, &rows, E * kCacheRow * elem, false));
+    DM_TRY(pool_alloc(p, &hits, T * kCacheRow * elem));
+    DM_TRY(pool_alloc(p, &v.pend_centry, T, false));
+    DM_TRY(pool_alloc(p, &v.pend_cctl, T));
+    DM_CUDA(cudaMemset(v.pend_centry, 0xff, T * sizeof(int)));
+    v.crow = rows;
+    v.hit_row = hits;
+    v.cmask = (u32)(E - 1);
+    v.cache_f64 = is_f64 ? 1 : 0;
+    v.cctl = ctl;   // last: a non-null cctl switches the cache on in the kernels
+    return DM_OK;
+}
+
+extern "C" int dm_pool_cache_clear(dm_pool* p, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_cache_clear: null pool");
+    if (!p->v.cctl) return DM_OK;
+    // entries that are pending right now are dropped as well: their owners find another ctl word and skip the store
+    DM_CUDA(cudaMemsetAsync(p->v.cctl, 0, ((size_t)p->v.cmask + 1) * sizeof(unsigned long long), (cudaStream_t)stream));
+    return DM_OK;
+}
+
+extern "C" int dm_pool_leaf_index(dm_pool* p, int32_t** index) {
+    DM_CHECK_ARG(p && index, "dm_pool_leaf_index: null argument");
+    *index = p->v.leaf_index;
+    return DM_OK;
+}
+
+extern "C" int dm_eval_hashed(int game, int grid, int n, const int32_t* count_dev, const int32_t* index_dev,
+                              const uint64_t* first, const uint64_t* second, const uint8_t* player, uint64_t salt,
+                              double* value, double* probs, void* stream) {
+    DM_CHECK_ARG(game_cfg_valid(game, grid), "dm_eval_hashed: unsupported game/grid");
+    DM_CHECK_ARG(n >= 0, "negative batch size");
+    if (n == 0) return DM_OK;
+    DM_CHECK_ARG(first && second && player && value && probs, "dm_eval_hashed: bad arguments");
+    k_eval_hashed<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(make_game_cfg(game, grid), n, count_dev, index_dev,
+                                                                     (const u64*)first, (const u64*)second, player,
+                                                                     (u64)salt, value, probs);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
 extern "C" int dm_pool_leaf_buffers(dm_pool* p, uint64_t** first, uint64_t** second, uint8_t** player,
                                     int32_t** tree, int32_t** count) {
     DM_CHECK_ARG(p, "dm_pool_leaf_buffers: null pool");
@@ -1543,6 +1890,8 @@ extern "C" int dm_pool_expand_backup(dm_pool* p, const void* priors, int stride,
                                      void* stream) {
     DM_CHECK_ARG(p && priors && values, "dm_pool_expand_backup: null argument");
     DM_CHECK_ARG(stride >= p->v.cfg.num_actions, "dm_pool_expand_backup: prior_stride < num_actions");
+    DM_CHECK_ARG(!p->v.cctl || p->v.leaves_per_round > 1 || p->v.cache_f64 == (is_f64 ? 1 : 0),
+                 "dm_pool_expand_backup: evaluator output type differs from the evaluation cache's");
     if (p->v.leaves_per_round > 1) {
         if (is_f64)
             k_expand_backup_vl<double><<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
@@ -1567,6 +1916,8 @@ extern "C" int dm_pool_round(dm_pool* p, const void* priors, int stride, const v
                              void* stream) {
     DM_CHECK_ARG(p && priors && values, "dm_pool_round: null argument");
     DM_CHECK_ARG(stride >= p->v.cfg.num_actions, "dm_pool_round: prior_stride < num_actions");
+    DM_CHECK_ARG(!p->v.cctl || p->v.cache_f64 == (is_f64 ? 1 : 0),
+                 "dm_pool_round: evaluator output type differs from the evaluation cache's");
     if (!p->configured || p->v.eval_kind != DM_EVAL_EXTERNAL || p->v.leaves_per_round != 1) {
         dm_set_error("dm_pool_round: needs eval_kind EXTERNAL and leaves_per_round 1");
         return DM_ERR_STATE;
@@ -1605,6 +1956,13 @@ extern "C" int dm_pool_root_children(dm_pool* p, uint8_t* order, int32_t* count_
     return DM_OK;
 }
 
+extern "C" int dm_pool_root_child_stats(dm_pool* p, double* prior, double* value_sum, void* stream) {
+    DM_CHECK_ARG(p, "dm_pool_root_child_stats: null pool");
+    k_root_child_stats<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v, prior, value_sum);
+    DM_LAUNCH_CHECK();
+    return DM_OK;
+}
+
 extern "C" int dm_pool_advance(dm_pool* p, const int32_t* actions, void* stream) {
     DM_CHECK_ARG(p && actions, "dm_pool_advance: null argument");
     k_advance<<<tree_blocks(p->v.n_trees), kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(p->v, actions);
@@ -1626,7 +1984,9 @@ extern "C" int dm_pool_counters(dm_pool* p, uint64_t out[16]) {
     DM_CUDA(cudaSetDevice(p->cfg.device));
     DM_CUDA(cudaDeviceSynchronize());
     DM_CUDA(cudaMemcpy(out, p->v.counters, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
-    if (out[kCntCapacity]) {
+    if (out[kCntCapacity] > p->capacity_errors_reported) {
+        // reported once per new error: the counter itself stays in out[8], later calls succeed again
+        p->capacity_errors_reported = out[kCntCapacity];
         dm_set_error("a tree ran out of node or path capacity (raise max_nodes_per_tree)");
         return DM_ERR_CAPACITY;
     }
@@ -1649,6 +2009,7 @@ extern "C" int dm_selfplay_enable(dm_pool* p, int replay_capacity) {
     DM_TRY(pool_alloc(p, &v.rp_pi, R * DM_MAX_ACTIONS));
     DM_TRY(pool_alloc(p, &v.rp_z, R));
     DM_TRY(pool_alloc(p, &v.rp_written, 1));
+    DM_TRY(pool_alloc(p, &v.rp_game_end, (size_t)DM_REPLAY_GAME_RING));
     v.replay_cap = R;
     v.selfplay = 1;
     return DM_OK;
@@ -1672,5 +2033,11 @@ extern "C" int dm_selfplay_replay(dm_pool* p, uint64_t** first, uint64_t** secon
     if (pi) *pi = p->v.rp_pi;
     if (z) *z = p->v.rp_z;
     if (written) *written = (uint64_t*)p->v.rp_written;
+    return DM_OK;
+}
+
+extern "C" int dm_selfplay_games(dm_pool* p, uint64_t** game_end) {
+    DM_CHECK_ARG(p && p->v.selfplay && game_end, "dm_selfplay_games: self-play not enabled");
+    *game_end = (uint64_t*)p->v.rp_game_end;
     return DM_OK;
 }

@@ -37,6 +37,7 @@ class DeviceNet:
         _lib.call("dm_net_create", cfg, handle)
         self._h = handle
         self._loaded = False
+        self.weights_version = 0     # bumped by load_state_dict: evaluation caches of older weights are stale
         A = _lib.DM_MAX_ACTIONS
         # outputs of the search path: a fused round leaves its last batch pending here until the next round
         self._value = torch.zeros(self.max_batch, dtype=torch.float32, device=self.device)
@@ -66,6 +67,7 @@ class DeviceNet:
         with torch.cuda.device(self.device):
             _lib.call("dm_net_finalize", self._h, current_stream())
         self._loaded = True
+        self.weights_version += 1
 
     # ------------------------------------------------------------------------ inference
     def _check(self, n: int) -> None:
@@ -84,6 +86,18 @@ class DeviceNet:
         with torch.cuda.device(self.device):
             _lib.call("dm_net_evaluate", self._h, prec, int(n), count_dev.data_ptr() if count_dev is not None else 0,
                       first.data_ptr(), second.data_ptr(), player.data_ptr(), self._value.data_ptr(),
+                      self._probs.data_ptr(), current_stream())
+        return self._value, self._probs
+
+    def evaluate_indexed(self, pool) -> Tuple[torch.Tensor, torch.Tensor]:
+        """Evaluate a dense leaf batch through its compacted index (``pool.leaf_index`` / ``pool.leaf_count``,
+        written by ``pool.round(selfplay=True)``): only the slots that need the network are run, every result
+        lands in its own slot of the output buffers."""
+        self._check(pool.n_trees)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_net_evaluate_indexed", self._h, PRECISIONS[self.precision], int(pool.n_trees),
+                      pool.leaf_count.data_ptr(), pool.leaf_index.data_ptr(), pool.leaf_first.data_ptr(),
+                      pool.leaf_second.data_ptr(), pool.leaf_player.data_ptr(), self._value.data_ptr(),
                       self._probs.data_ptr(), current_stream())
         return self._value, self._probs
 
@@ -173,7 +187,11 @@ class DeviceNet:
             if timers is not None:
                 ev[1].record()
                 timers.append(("tree_round", ev[0], ev[1]))
-            self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity, pool.leaf_count)
+            if selfplay:
+                self.evaluate_indexed(pool)     # dense batch: slot t belongs to tree t, live slots are listed
+            else:
+                self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity,
+                                     pool.leaf_count)
             return
         if timers is not None:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -196,8 +214,11 @@ class DeviceNet:
 
     def evaluate_pending(self, pool) -> None:
         """Network evaluation + expand/backup of the leaves a previous select left pending."""
-        value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity,
-                                            pool.leaf_count)
+        if pool.dense_batch:
+            value, probs = self.evaluate_indexed(pool)
+        else:
+            value, probs = self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player,
+                                                pool.leaf_capacity, pool.leaf_count)
         pool.expand_backup(probs, value)
 
     def run_search(self, pool, sims: int, round_graph=None) -> None:

@@ -19,6 +19,11 @@ def world() -> Tuple[int, int]:
     return 0, 1
 
 
+def barrier() -> None:
+    if world()[1] > 1:
+        dist.barrier()
+
+
 def shard_games(total_games: int, world_size: int, rank: int) -> int:
     """Games owned by ``rank`` when ``total_games`` are dealt round-robin (game i -> rank i % world)."""
     return total_games // world_size + (1 if rank < total_games % world_size else 0)
@@ -32,9 +37,71 @@ def reduce_counters(sums: Dict[str, float], maxima: Dict[str, float], device) ->
         return dict(sums), dict(maxima)
     s = torch.tensor([float(v) for v in sums.values()], dtype=torch.float64, device=device)
     m = torch.tensor([float(v) for v in maxima.values()], dtype=torch.float64, device=device)
-    dist.all_reduce(s, op=dist.ReduceOp.SUM)
-    dist.all_reduce(m, op=dist.ReduceOp.MAX)
+    if sums:
+        dist.all_reduce(s, op=dist.ReduceOp.SUM)
+    if maxima:
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
     return dict(zip(sums.keys(), s.tolist())), dict(zip(maxima.keys(), m.tolist()))
+
+
+def _allreduce_mean(flat: torch.Tensor, size: int) -> None:
+    """In-place mean over ranks; NCCL averages inside the collective, gloo needs the division."""
+    if dist.get_backend() == "nccl":
+        dist.all_reduce(flat, op=dist.ReduceOp.AVG)
+    else:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        flat /= size
+
+
+class GradientBucket:
+    """All gradients of a module as views into ONE persistent flat buffer, so the data-parallel step is a
+    single in-place all-reduce with no flatten / unflatten copies around it (1 579 845 floats =
+    6.3 MB for the Othello 8x8 net, latency-bound over NVLink, so one bucket is the right shape).
+    Autograd accumulates into an existing ``.grad`` in place, so the views survive ``backward()``;
+    clear them with ``zero()`` (``optimizer.zero_grad()`` would drop them)."""
+
+    def __init__(self, parameters: Iterable[torch.nn.Parameter]) -> None:
+        self.params = [p for p in parameters if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        first = self.params[0]
+        self.flat = torch.zeros(total, dtype=first.dtype, device=first.device)
+        offset = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[offset:offset + n].view_as(p)
+            offset += n
+
+    def zero(self) -> None:
+        self.flat.zero_()
+
+    def attached(self) -> bool:
+        """False once something replaced a ``.grad`` (e.g. ``zero_grad(set_to_none=True)``)."""
+        base = self.flat.untyped_storage().data_ptr()
+        return all(p.grad is not None and p.grad.untyped_storage().data_ptr() == base for p in self.params)
+
+    def allreduce(self) -> int:
+        rank, size = world()
+        if size > 1:
+            _allreduce_mean(self.flat, size)
+        return self.flat.numel()
+
+
+def allreduce_buffers(module: torch.nn.Module) -> int:
+    """Average the floating-point buffers (BatchNorm running_mean / running_var) over all ranks in one flat
+    all-reduce.  Every rank trains on its own shard of the batch, so the running statistics drift apart;
+    averaging them at each weight transfer keeps the replicas' self-play networks identical."""
+    rank, size = world()
+    bufs = [b for b in module.buffers() if b.is_floating_point()]
+    if size == 1 or not bufs:
+        return sum(b.numel() for b in bufs)
+    flat = torch.cat([b.reshape(-1) for b in bufs])
+    _allreduce_mean(flat, size)
+    offset = 0
+    for b in bufs:
+        n = b.numel()
+        b.copy_(flat[offset:offset + n].view_as(b))
+        offset += n
+    return offset
 
 
 def allreduce_gradients(parameters: Iterable[torch.nn.Parameter]) -> int:

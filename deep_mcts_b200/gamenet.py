@@ -59,6 +59,8 @@ class GameNet(ABC):
         # optional hook run between backward() and optimizer.step(), e.g.
         # deep_mcts_b200.distributed.allreduce_gradients for data-parallel training
         self.grad_sync: Optional[Callable] = None
+        # deep_mcts_b200.distributed.GradientBucket: gradients as views into one flat buffer, all-reduced in place
+        self.grad_bucket = None
         self.max_batch = 4096
         # lets MCTS recognise `net.evaluate` as a device evaluator
         self._dm_net_self = self
@@ -111,9 +113,16 @@ class GameNet(ABC):
         policy_loss = self.policy_criterion(logits, probability_targets)
         value_loss = self.value_criterion(values, value_targets)
         acc = accuracy(logits, probability_targets)
-        self.optimizer.zero_grad()
+        bucket = self.grad_bucket
+        if bucket is not None and bucket.attached():
+            bucket.zero()                       # gradients live in one flat buffer: keep the views
+        else:
+            bucket = None
+            self.optimizer.zero_grad()
         (policy_loss + value_loss).backward()
-        if self.grad_sync is not None:
+        if bucket is not None:
+            bucket.allreduce()
+        elif self.grad_sync is not None:
             self.grad_sync(self.net.parameters())
         self.optimizer.step()
         self._device_net_stale = True

@@ -161,9 +161,19 @@ class BatchedMCTS:
             if self._eval_kind != _lib.DM_EVAL_EXTERNAL:
                 self._host_eval = self.state_evaluator or None
                 self._eval_kind = _lib.DM_EVAL_EXTERNAL
+        if (self._net is not None and getattr(ev, "_dm_net", None) is not None and self._greedy_net is None
+                and self._host_rollout is None and self.leaves_per_round == 1):
+            # cached_state_evaluator(net) (reference train.py:408-414): memoise on the device.  (The policy-network
+            # rollout path and host rollouts drive the leaf exchange themselves and evaluate every leaf.)
+            work = self.pool.n_trees * (int(self.num_simulations) if self.num_simulations != float("inf") else 4096)
+            self.pool.enable_cache(min(22, max(14, (8 * work).bit_length())), torch.float32)
+            self._cache_weights_version = None
 
     def _configure(self, sims: int, alpha: Optional[float] = None) -> None:
         vl = self.leaves_per_round if self._eval_kind == _lib.DM_EVAL_EXTERNAL and self._greedy_net is None else 1
+        if vl > 1 and self._rollout_kind != _lib.DM_ROLLOUT_NONE:
+            # the virtual-loss kernels back up the evaluator's value only (no evaluate_leaf mixing, mcts.py:187-196)
+            raise ValueError("leaves_per_round > 1 (virtual-loss mode) does not support rollout policies")
         self.pool.configure(sims, self._eval_kind, self._rollout_kind, self.sample_move_cutoff,
                             self.dirichlet_alpha if alpha is None else alpha, self.dirichlet_factor,
                             self.rollout_share, self._salt, vl)
@@ -172,9 +182,15 @@ class BatchedMCTS:
     def _host_evaluate(self, player, first, second):
         m = self.game_manager
         values, priors = [], []
-        for p, f, s in zip(player, first, second):
+        net_values = net_probs = None
+        if self._host_eval is None and self._net is not None:
+            # GameNet evaluator next to a Python rollout policy: the network still runs as one device batch
+            net_values, net_probs = self._net.evaluate_batch(player, first, second)
+        for i, (p, f, s) in enumerate(zip(player, first, second)):
             state = m._make_state(p, f, s)
-            if self._host_eval is not None:
+            if net_values is not None:
+                value, probs = float(net_values[i]), [float(x) for x in net_probs[i]]
+            elif self._host_eval is not None:
                 value, probs = self._host_eval(state)
                 probs = [float(x) for x in probs]
                 assert len(probs) == m.num_actions
@@ -206,7 +222,12 @@ class BatchedMCTS:
             self._run_greedy_rollout_search(sims)
         elif self._eval_kind != _lib.DM_EVAL_EXTERNAL:
             self.pool.search_local()
-        elif self._net is not None:
+        elif self._net is not None and self._host_rollout is None:
+            if self.pool.cache_entries:
+                version = self._net.device_net().weights_version
+                if version != self._cache_weights_version:      # the network was re-trained: forget its old outputs
+                    self.pool.cache_clear()
+                    self._cache_weights_version = version
             self._net.run_search(self.pool, sims)
         else:
             self.pool.step_external(self._host_evaluate, max_rounds=sims + 2)
@@ -280,9 +301,12 @@ class MCTS(BatchedMCTS):
     def root(self) -> Node:
         order, count, root_visits = self.pool.root_children()
         visits, _ = self.pool.root_visits()
+        prior, value_sum = self.pool.root_child_stats()
         node = Node(int(root_visits[0]))
-        for a in order[0, : int(count[0])]:
-            node.children[int(a)] = Node(int(visits[0, int(a)]))
+        for j, a in enumerate(order[0, : int(count[0])]):
+            child = Node(int(visits[0, int(a)]), float(prior[0, j]))
+            child.value_sum = float(value_sum[0, j])
+            node.children[int(a)] = child
         return node
 
     def step(self) -> Tuple[List[float], Tuple[int, int]]:

@@ -65,6 +65,12 @@ class TreePool:
         self.leaf_player = wrap_device_buffer(ptrs[2].value, (cap,), torch.uint8, self.device)
         self.leaf_tree = wrap_device_buffer(ptrs[3].value, (cap,), torch.int32, self.device)
         self.leaf_count = wrap_device_buffer(ptrs[4].value, (1,), torch.int32, self.device)
+        idx = _lib.c_void_p()
+        _lib.call("dm_pool_leaf_index", self._h, idx)
+        # dense batches (round(selfplay=True)): the slots whose leaf needs the evaluator, compacted; count in leaf_count
+        self.leaf_index = wrap_device_buffer(idx.value, (T,), torch.int32, self.device)
+        self.cache_entries = 0
+        self.dense_batch = False    # the pending leaf batch is dense (slot = tree) and must be read through leaf_index
         self._visits = torch.zeros((T, _lib.DM_MAX_ACTIONS), dtype=torch.int32, device=self.device)
         self._stats = torch.zeros((T, 2), dtype=torch.int32, device=self.device)
 
@@ -92,6 +98,20 @@ class TreePool:
         _lib.call("dm_pool_configure", self._h, sc)
         self._search = sc
         self.leaves_per_round = max(1, int(leaves_per_round))
+
+    def enable_cache(self, log2_entries: int = 22, dtype: torch.dtype = torch.float32) -> None:
+        """Device-side ``cached_state_evaluator`` (reference train.py:408-414): memoise the external evaluator's
+        outputs per state in a 2**log2_entries-entry table and evaluate equal leaves of one round once.
+        Result-transparent for a fixed evaluator; ``dtype`` is the evaluator's output type."""
+        assert dtype in (torch.float32, torch.float64)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_cache_enable", self._h, int(log2_entries), 1 if dtype == torch.float64 else 0)
+        self.cache_entries = 1 << int(log2_entries)
+
+    def cache_clear(self) -> None:
+        """Forget every cached evaluation (after a weight transfer)."""
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_cache_clear", self._h, self._stream())
 
     @property
     def leaf_capacity(self) -> int:
@@ -163,6 +183,7 @@ class TreePool:
     def select(self) -> None:
         with torch.cuda.device(self.device):
             _lib.call("dm_pool_select", self._h, self._stream())
+        self.dense_batch = False
 
     def expand_backup(self, priors: torch.Tensor, values: torch.Tensor) -> None:
         assert priors.is_cuda and values.is_cuda and priors.dtype == values.dtype
@@ -182,6 +203,7 @@ class TreePool:
         with torch.cuda.device(self.device):
             _lib.call("dm_pool_round", self._h, priors.data_ptr(), int(priors.shape[1]), values.data_ptr(),
                       1 if priors.dtype == torch.float64 else 0, 1 if selfplay else 0, self._stream())
+        self.dense_batch = bool(selfplay)
 
     def step_external(self, evaluate: Callable[[np.ndarray, np.ndarray, np.ndarray], Tuple[np.ndarray, np.ndarray]],
                       max_rounds: Optional[int] = None) -> None:
@@ -225,6 +247,16 @@ class TreePool:
                       self._stream())
         return order.cpu().numpy(), count.cpu().numpy(), rv.cpu().numpy()
 
+    def root_child_stats(self) -> Tuple[np.ndarray, np.ndarray]:
+        """(prior[n_trees, 65], value_sum[n_trees, 65]) of the root's children in child order: ``Node.probability``
+        (after the Dirichlet mixing of mcts.py:233-241) and ``Node.value_sum``."""
+        T = self.n_trees
+        prior = torch.empty((T, _lib.DM_MAX_ACTIONS), dtype=torch.float64, device=self.device)
+        vsum = torch.empty((T, _lib.DM_MAX_ACTIONS), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("dm_pool_root_child_stats", self._h, prior.data_ptr(), vsum.data_ptr(), self._stream())
+        return prior.cpu().numpy(), vsum.cpu().numpy()
+
     def advance(self, actions) -> None:
         a = torch.from_numpy(np.asarray(actions, dtype=np.int32)).to(self.device)
         assert a.numel() == self.n_trees
@@ -247,7 +279,7 @@ class TreePool:
 
     COUNTER_NAMES = ("simulations", "leaf_evals", "terminal_sims", "nodes_high_water", "games", "depth_sum",
                      "children_scanned", "children_created", "capacity_errors", "moves", "rollout_plies",
-                     "invalid_actions", "compactions")
+                     "invalid_actions", "compactions", "cache_hits", "cache_aliases", "cache_inserts")
 
     def counters(self) -> dict:
         out = (_lib.c_uint64 * 16)()
@@ -268,8 +300,31 @@ class TreePool:
         self.replay_player = wrap_device_buffer(ptrs[2].value, (R,), torch.uint8, self.device)
         self.replay_pi = wrap_device_buffer(ptrs[3].value, (R, _lib.DM_MAX_ACTIONS), torch.float32, self.device)
         self.replay_z = wrap_device_buffer(ptrs[4].value, (R,), torch.float32, self.device)
-        self.replay_written = wrap_device_buffer(ptrs[5].value, (1,), torch.int64, self.device)
+        # counter word: positions written (low DM_REPLAY_POS_BITS bits) | games written (bits above)
+        self.replay_counter = wrap_device_buffer(ptrs[5].value, (1,), torch.int64, self.device)
+        ge = _lib.c_void_p()
+        _lib.call("dm_selfplay_games", self._h, ge)
+        self.replay_game_end = wrap_device_buffer(ge.value, (_lib.DM_REPLAY_GAME_RING,), torch.int64, self.device)
+
+    def replay_progress(self) -> Tuple[int, int]:
+        """(positions, games) appended to the replay ring so far (synchronises)."""
+        word = int(self.replay_counter.item())
+        return word & ((1 << _lib.DM_REPLAY_POS_BITS) - 1), word >> _lib.DM_REPLAY_POS_BITS
+
+    def positions_written(self) -> int:
+        return self.replay_progress()[0]
+
+    def replay_window_start(self, max_games: int) -> int:
+        """Position (monotonic index) where the last ``max_games`` finished games begin -- the reference
+        trims its replay buffer to that many GAMES (train.py:149-151).  0 while fewer have been played."""
+        positions, games = self.replay_progress()
+        if max_games <= 0 or games <= max_games:
+            return 0
+        if max_games >= _lib.DM_REPLAY_GAME_RING:
+            return 0
+        return int(self.replay_game_end[(games - max_games - 1) % _lib.DM_REPLAY_GAME_RING].item())
 
     def selfplay_select(self) -> None:
         with torch.cuda.device(self.device):
             _lib.call("dm_selfplay_select", self._h, self._stream())
+        self.dense_batch = False

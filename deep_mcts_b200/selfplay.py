@@ -21,8 +21,12 @@ class BatchedSelfPlay:
     def __init__(self, net, n_trees: int, num_simulations: int, sample_move_cutoff: int = 0,
                  dirichlet_alpha: float = 0.0, dirichlet_factor: float = 0.25, replay_capacity: int = 1 << 20,
                  seed: int = 0, max_nodes_per_tree: Optional[int] = None, n_pools: int = 1,
-                 pool_sizes: Optional[Sequence[int]] = None) -> None:
+                 pool_sizes: Optional[Sequence[int]] = None, eval_cache_log2: Optional[int] = 22) -> None:
         """``net`` is a GameNet (its weights are used) or a DeviceNet.
+
+        ``eval_cache_log2``: size (log2 entries) of each pool's device evaluation cache -- the reference's
+        self-play workers evaluate through ``cached_state_evaluator`` (train.py:258-266, 408-414); ``None``
+        evaluates every leaf.  Search results are identical either way.
 
         ``n_pools`` > 1 splits the games into independent pools, each with its own network
         buffers and CUDA stream.  The pools' rounds are dependency chains of their own, so the
@@ -51,6 +55,8 @@ class BatchedSelfPlay:
             pool.configure(num_simulations, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, sample_move_cutoff,
                            dirichlet_alpha, dirichlet_factor)
             pool.enable_selfplay(max(1, replay_capacity * pool_sizes[i] // n_trees))
+            if eval_cache_log2 is not None:
+                pool.enable_cache(eval_cache_log2, torch.float32)
             self.pools.append(pool)
         if isinstance(net, DeviceNet):
             if n_pools != 1:
@@ -80,11 +86,25 @@ class BatchedSelfPlay:
             self.device_nets.append(dn)
 
     def sync_weights(self) -> None:
-        """Re-pack the GameNet's current weights into every pool's kernels (weight transfer)."""
+        """Re-pack the GameNet's current weights into every pool's kernels (weight transfer, reference
+        train.py:169-171).  The captured round graph is dropped -- the trunk kernels take the folded
+        biases and the value head's 1x1 weights as by-value arguments, which a capture freezes -- and the
+        evaluation caches are cleared (they memoise the old network)."""
+        if self._phase_offset:
+            for dn, pool in zip(self.device_nets[1:], self.pools[1:]):
+                dn.evaluate_pending(pool)           # finish the half-done round with the weights it was started with
+            self._phase_offset = False
         if not isinstance(self.net, DeviceNet):
             sd = self.net.net.state_dict()
             for dn in self.device_nets:
                 dn.load_state_dict(sd)
+        self.invalidate_weights()
+
+    def invalidate_weights(self) -> None:
+        """Call after the device network's weights changed behind this engine's back (a shared DeviceNet)."""
+        self._graph = None
+        for pool in self.pools:
+            pool.cache_clear()
 
     def run_rounds(self, rounds: int) -> None:
         """``rounds`` search rounds for every pool.  A single pool runs fused rounds (expand + backup of the
@@ -185,51 +205,54 @@ class BatchedSelfPlay:
         return total
 
     def positions_written(self) -> int:
-        return sum(int(pool.replay_written.item()) for pool in self.pools)
+        return sum(pool.positions_written() for pool in self.pools)
 
     def sample_batch(self, batch_size: int, generator: Optional[torch.Generator] = None,
-                     written: Optional[Sequence[int]] = None, skip_oldest: int = 0
+                     max_games: Optional[int] = None
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
-        """Uniform sample over the replay rings: (first, second, player, pi[B, A], z[B, 1]) on the device
-        (reference train.py:337-348 samples uniformly over positions).
+        """Uniform sample over the replay rings: (first, second, player, pi[B, A], z[B, 1]) on the device.
+        The reference picks a game with probability proportional to its length, then one of its positions
+        (train.py:337-348): uniform over positions.  ``max_games`` restricts the sample to the positions of
+        the last ``max_games`` finished games (the reference trims its buffer to ``replay_buffer_max_size``
+        GAMES, train.py:149-151); with several pools every pool contributes its share of that window.
 
-        ``written`` (positions written per pool, e.g. from ``positions_written_per_pool()`` at a moment
-        when self-play was idle) restricts the sample to positions that were complete at that moment;
-        ``skip_oldest`` additionally leaves out that many of each ring's oldest positions -- the ones
-        self-play may be overwriting while the sample is taken on another stream."""
-        if written is None:
-            written = self.positions_written_per_pool()
+        The sample reads the rings on the current stream: take it while self-play is idle (or ordered before
+        it on the same stream), never concurrently with ``run_rounds`` on another stream."""
         dev = self.pool.device
         A = self.pool.num_actions
-        parts = []
-        for pool, w in zip(self.pools, written):
-            cap = pool.replay_capacity
-            n = min(int(w), cap)
-            if n <= 0:
-                continue
-            if w > cap and skip_oldest > 0:
-                # ring is full: slots [head, head + skip) are the next to be overwritten
-                head = int(w) % cap
-                keep = torch.arange(n, device=dev)
-                keep = keep[((keep - head) % cap) >= min(skip_oldest, cap - 1)]
-            else:
-                keep = torch.arange(n, device=dev)
-            parts.append((pool, keep))
-        total = sum(int(k.numel()) for _, k in parts)
+        ranges = []
+        for pool, size in zip(self.pools, self.pool_sizes):
+            hi, _ = pool.replay_progress()
+            lo = max(0, hi - pool.replay_capacity)
+            if max_games is not None:
+                lo = max(lo, pool.replay_window_start(max(1, int(max_games) * size // self.n_trees)))
+            if hi > lo:
+                ranges.append((pool, lo, hi))
+        total = sum(hi - lo for _, lo, hi in ranges)
         if total == 0:
             raise RuntimeError("replay ring is empty")
         idx = torch.randint(0, total, (batch_size,), device=dev, generator=generator)
-        if len(parts) == 1:
-            pool, keep = parts[0]
-            sel = keep[idx]
+        if len(ranges) == 1:
+            pool, lo, _ = ranges[0]
+            sel = (idx + lo) % pool.replay_capacity
             return (pool.replay_first[sel], pool.replay_second[sel], pool.replay_player[sel], pool.replay_pi[sel, :A],
                     pool.replay_z[sel].unsqueeze(1))
-        first = torch.cat([p.replay_first[k] for p, k in parts])
-        second = torch.cat([p.replay_second[k] for p, k in parts])
-        player = torch.cat([p.replay_player[k] for p, k in parts])
-        pi = torch.cat([p.replay_pi[k, :A] for p, k in parts])
-        z = torch.cat([p.replay_z[k] for p, k in parts])
-        return first[idx], second[idx], player[idx], pi[idx], z[idx].unsqueeze(1)
+        first = torch.empty(batch_size, dtype=torch.int64, device=dev)
+        second = torch.empty(batch_size, dtype=torch.int64, device=dev)
+        player = torch.empty(batch_size, dtype=torch.uint8, device=dev)
+        pi = torch.empty((batch_size, A), dtype=torch.float32, device=dev)
+        z = torch.empty(batch_size, dtype=torch.float32, device=dev)
+        offset = 0
+        for pool, lo, hi in ranges:
+            mine = (idx >= offset) & (idx < offset + (hi - lo))
+            sel = (idx[mine] - offset + lo) % pool.replay_capacity
+            first[mine], second[mine], player[mine] = pool.replay_first[sel], pool.replay_second[sel], pool.replay_player[sel]
+            pi[mine], z[mine] = pool.replay_pi[sel, :A], pool.replay_z[sel]
+            offset += hi - lo
+        return first, second, player, pi, z.unsqueeze(1)
+
+    def games_written(self) -> int:
+        return sum(pool.replay_progress()[1] for pool in self.pools)
 
     def positions_written_per_pool(self):
-        return [int(pool.replay_written.item()) for pool in self.pools]
+        return [pool.positions_written() for pool in self.pools]

@@ -106,6 +106,8 @@ class SelfPlayTrainer:
         game_net.to(self.device)
         dd.broadcast_parameters(game_net.net, 0)
         game_net.grad_sync = dd.allreduce_gradients
+        # gradients as views into one flat buffer: the data-parallel step is one in-place all-reduce
+        game_net.grad_bucket = dd.GradientBucket(game_net.net.parameters())
         game_net.precision = config.precision
         self.transpose = manager.game_id in (_lib.DM_HEX, _lib.DM_HEX_SWAP)
         positions = config.replay_buffer_max_size * (manager.board * manager.board)
@@ -119,8 +121,6 @@ class SelfPlayTrainer:
         self.generator.manual_seed(1234 + self.rank)
         self.engine.use_graph = True
         self.sp_stream = torch.cuda.Stream(device=self.device) if config.overlap_training else None
-        self._sample_written = None      # replay positions that were complete when self-play was last idle
-        self._skip_oldest = 0
 
     # ---- self-play -------------------------------------------------------------------
     def _uniform_round(self) -> None:
@@ -143,34 +143,42 @@ class SelfPlayTrainer:
         else:
             self.engine.run_rounds(rounds)
 
+    def have_examples(self) -> bool:
+        """Collective: True once EVERY rank has replay positions to train on (ranks must take the same number
+        of all-reduced SGD steps, so the decision cannot be rank-local)."""
+        mine = 1.0 if self.engine.positions_written() > 0 else 0.0
+        sums, _ = dd.reduce_counters({"have": mine}, {}, self.device)
+        return sums["have"] >= self.world
+
     def block(self, train_steps: int):
         """One block of the loop: ``num_simulations`` search rounds for every game and ``train_steps`` SGD steps.
-        With ``overlap_training`` the two run concurrently on two streams: the steps sample only replay
-        positions that were complete when the block started (minus the ring slots this block's self-play may
-        overwrite), and the weight transfer happens at the block boundary, when both streams are idle.
+        With ``overlap_training`` the two run concurrently on two streams.  The steps' batches are gathered from
+        the replay ring BEFORE the block's self-play is launched, so the SGD stream never reads a ring slot the
+        search is overwriting; the weight transfer happens at the block boundary, when both streams are idle.
         Returns the list of (policy_loss, value_loss, accuracy) of the steps taken."""
         if self.sp_stream is None or self.uniform_phase:
             self.self_play_block()
-            return [self.train_step() for _ in range(train_steps)] if self.engine.positions_written() else []
+            return [self.train_step() for _ in range(train_steps)] if self.have_examples() else []
         main = torch.cuda.current_stream()
-        self._sample_written = self.engine.positions_written_per_pool()
-        # a block finishes at most one move per tree per (num_simulations + 1) rounds, and a few more for short games
-        self._skip_oldest = 2 * self.config.n_trees
+        batches = [self.sample() for _ in range(train_steps)] if self.have_examples() else []
         self.sp_stream.wait_stream(main)
         with torch.cuda.stream(self.sp_stream):
             self.self_play_block()
-        losses = [self.train_step(defer_transfer=True) for _ in range(train_steps)] if sum(self._sample_written) else []
+        losses = [self.train_step(batch, defer_transfer=True) for batch in batches]
         main.wait_stream(self.sp_stream)
-        self._sample_written = None
         if self._transfer_due:
             self._transfer_weights()
         return losses
 
     # ---- training --------------------------------------------------------------------
-    def train_step(self, defer_transfer: bool = False):
-        first, second, player, pi, z = self.engine.sample_batch(self.config.batch_size, self.generator,
-                                                                written=self._sample_written,
-                                                                skip_oldest=self._skip_oldest if self._sample_written else 0)
+    def sample(self):
+        """One training batch from the last ``replay_buffer_max_size`` games (train.py:149-151, 337-348);
+        every rank holds its share of that window."""
+        return self.engine.sample_batch(self.config.batch_size, self.generator,
+                                        max_games=max(1, self.config.replay_buffer_max_size // self.world))
+
+    def train_step(self, batch=None, defer_transfer: bool = False):
+        first, second, player, pi, z = batch if batch is not None else self.sample()
         planes = bitboards_to_planes(first, second, player, self.net.manager.board, self.transpose)
         if pi.shape[1:] != tuple(self.net.net.policy_head.out_shape):
             pi = pi.reshape(pi.shape[0], *self.net.net.policy_head.out_shape)
@@ -186,13 +194,19 @@ class SelfPlayTrainer:
     _transfer_due = False
 
     def _transfer_weights(self) -> None:
-        """Weight transfer to the self-play kernels (train.py:169-171)."""
+        """Weight transfer to the self-play kernels (train.py:169-171).  Parameters are identical on every rank
+        (same start, same averaged gradients); the BatchNorm running statistics are not -- each rank normalises
+        its own shard of the batch -- so they are averaged here, which keeps the replicas' self-play networks
+        identical."""
+        dd.allreduce_buffers(self.net.net)
         self.engine.sync_weights()
         self.uniform_phase = False
         self._transfer_due = False
 
     def games_finished(self) -> int:
-        return self.engine.counters()["games"]
+        """Games finished on ALL ranks (collective)."""
+        sums, _ = dd.reduce_counters({"games": self.engine.games_written()}, {}, self.device)
+        return int(sums["games"])
 
 
 def _train(game_net: GameNet, config: TrainingConfiguration) -> Iterable[Tuple[int, int, AgentComparison, AgentComparison]]:
@@ -206,10 +220,15 @@ def _train(game_net: GameNet, config: TrainingConfiguration) -> Iterable[Tuple[i
             net_parameters["optimizer_cls"] = net_parameters["optimizer_cls"].__name__
             json.dump({"net_parameters": net_parameters, "training_configuration": config.to_json_dict()}, f, indent=2)
     previous = game_net.copy().to(trainer.device)
-    target_games = max(1, config.num_games * config.nprocs // world)
+    # the reference plays num_games per worker process; the stop condition is collective (the summed game count),
+    # so every rank runs the same number of blocks and of all-reduced SGD steps
+    target_games = max(1, config.num_games * config.nprocs)
     policy_loss = value_loss = acc = 0.0
-    while trainer.games_finished() < target_games:
-        for pl, vl, ac in trainer.block(config.train_steps_per_block):
+    games = 0
+    while games < target_games:
+        losses = trainer.block(config.train_steps_per_block)
+        games = trainer.games_finished()
+        for pl, vl, ac in losses:
             policy_loss, value_loss, acc = (policy_loss + pl.detach().item(), value_loss + vl.detach().item(),
                                              acc + ac.detach().item())
             it = trainer.iterations
@@ -218,12 +237,13 @@ def _train(game_net: GameNet, config: TrainingConfiguration) -> Iterable[Tuple[i
             if config.evaluation_interval and it % config.evaluation_interval == 0:
                 if rank == 0:
                     random_eval, previous_eval = evaluate(game_net, previous, game_net.manager, config)
-                    print(f"{time.strftime('%H:%M:%S')} iterations: {it} games: {trainer.games_finished()} "
+                    print(f"{time.strftime('%H:%M:%S')} iterations: {it} games: {games} "
                           f"previous: {previous_eval} random MCTS: {random_eval} "
                           f"policy_loss: {policy_loss / config.evaluation_interval:.2f} "
                           f"value_loss: {value_loss / config.evaluation_interval:.2f} "
                           f"accuracy: {acc / config.evaluation_interval:.2f}")
-                    yield it - 1, trainer.games_finished(), random_eval, previous_eval
+                    yield it - 1, games, random_eval, previous_eval
+                dd.barrier()    # the other ranks wait here, not inside the next gradient all-reduce
                 policy_loss = value_loss = acc = 0.0
                 previous.load_state_dict(game_net.net.state_dict())
 

@@ -43,6 +43,8 @@ extern "C" {
 #define DM_MAX_ACTIONS 65   /* 8x8 board + pass/swap */
 #define DM_MAX_DEPTH 128    /* longest root-to-leaf path / plies per game recorded */
 #define DM_MAX_LEAVES 8     /* leaves one tree may have in flight per round (virtual-loss mode) */
+#define DM_REPLAY_POS_BITS 38          /* replay counter word: positions written in the low bits, games above */
+#define DM_REPLAY_GAME_RING (1 << 18)  /* games whose end positions are remembered (replay window in games) */
 
 typedef enum {
     DM_OK = 0,
@@ -138,6 +140,14 @@ int dm_eval_uniform(int game, int grid, int n, const int32_t* count_dev, const u
                     const uint64_t* second_dev, const uint8_t* player_dev, float* value_dev, float* probs_dev,
                     void* stream);
 
+/* the DM_EVAL_HASHED test evaluator as an external one: value_dev[slot] and probs_dev[slot][DM_MAX_ACTIONS] in
+ * double for the live leaves; index_dev (may be NULL) lists the slots of a compacted dense batch
+ * (dm_pool_leaf_index).  Parity tests use it to drive the leaf-exchange kernels and the evaluation
+ * cache with an evaluator whose reference results are pinned. */
+int dm_eval_hashed(int game, int grid, int n, const int32_t* count_dev, const int32_t* index_dev,
+                   const uint64_t* first_dev, const uint64_t* second_dev, const uint8_t* player_dev, uint64_t salt,
+                   double* value_dev, double* probs_dev, void* stream);
+
 /* ------------------------------------------------------------------------ trees */
 int dm_pool_create(const dm_pool_config* cfg, dm_pool** out);
 int dm_pool_destroy(dm_pool* pool);
@@ -172,6 +182,22 @@ int dm_pool_select(dm_pool* pool, void* stream);
  * (capacity n_trees * DM_MAX_LEAVES entries) */
 int dm_pool_leaf_buffers(dm_pool* pool, uint64_t** first_dev, uint64_t** second_dev, uint8_t** player_dev,
                          int32_t** tree_dev, int32_t** count_dev);
+/* dense batches (dm_pool_round with selfplay != 0): tree t's leaf lives in slot t; index_dev[0..count) lists the
+ * slots whose leaf needs the evaluator this round, ascending (trees served by the evaluation cache, aliased to
+ * an equal leaf of the same round, or sitting the round out are left out).  Feed it to
+ * dm_net_evaluate_indexed. */
+int dm_pool_leaf_index(dm_pool* pool, int32_t** index_dev);
+/* cached_state_evaluator (train.py:408-414) on the device: a 2^log2_entries-entry table in HBM keyed by the
+ * state -> (priors[DM_MAX_ACTIONS], value) of the external evaluator, probed by every selection of
+ * dm_pool_select / dm_selfplay_select / dm_pool_round (exact mode).  A hit needs no evaluation (the leaf is
+ * expanded from the stored row at the next expand step), equal leaves of one round are evaluated once, and
+ * the evaluator's outputs are inserted when their leaves are expanded.  Result-transparent for a fixed
+ * evaluator: visit counts are bit-identical with and without it.  is_f64 selects the row type and must
+ * match the evaluator outputs later passed to dm_pool_expand_backup / dm_pool_round.  Call
+ * dm_pool_cache_clear after every weight transfer (the reference clears its lru_cache there,
+ * train.py:169-171 via a new worker net). */
+int dm_pool_cache_enable(dm_pool* pool, int log2_entries, int is_f64);
+int dm_pool_cache_clear(dm_pool* pool, void* stream);
 /* phase 2 (expand_node + rollout mix + backpropagate, mcts.py:186-231): values_dev[slot]
  * and priors_dev[slot][prior_stride] per pending leaf, as float (is_f64 = 0) or double. */
 int dm_pool_expand_backup(dm_pool* pool, const void* priors_dev, int prior_stride, const void* values_dev,
@@ -180,9 +206,10 @@ int dm_pool_expand_backup(dm_pool* pool, const void* priors_dev, int prior_strid
  * loop, mcts.py:119-138): every tree with a pending leaf expands it and backs it up from
  * values_dev / priors_dev (indexed by the slot the leaf was handed out in), then selects its next
  * leaf into the leaf buffers.  selfplay != 0 gives the selection dm_selfplay_select's move-making
- * (needs dm_selfplay_enable) and a DENSE leaf batch: tree t's leaf is always in slot t and the leaf
- * count is n_trees (a tree without a new leaf keeps its previous one there; its result is ignored),
- * which removes the shared slot counter from the hot loop.  Exact mode only (leaves_per_round 1).
+ * (needs dm_selfplay_enable) and a DENSE leaf batch: tree t's leaf is always in slot t, which removes the
+ * shared slot counter from the hot loop; the last block of the launch compacts the slots that need the
+ * evaluator into dm_pool_leaf_index and stores their number in the leaf count.  Exact mode only
+ * (leaves_per_round 1).
  * The evaluator outputs of the previous batch must stay untouched until this call has run. */
 int dm_pool_round(dm_pool* pool, const void* priors_dev, int prior_stride, const void* values_dev, int is_f64,
                   int selfplay, void* stream);
@@ -192,15 +219,21 @@ int dm_pool_root_visits(dm_pool* pool, uint32_t* visits_dev, uint32_t* stats_dev
 /* root.children iteration order and the root's own visit count; order_dev[n_trees][DM_MAX_ACTIONS] */
 int dm_pool_root_children(dm_pool* pool, uint8_t* order_dev, int32_t* count_dev, uint32_t* root_visits_dev,
                           void* stream);
+/* Node.probability (after Dirichlet mixing, mcts.py:233-241) and Node.value_sum (mcts.py:27-54) of the root's
+ * children in child order, [n_trees][DM_MAX_ACTIONS] doubles each; either pointer may be NULL */
+int dm_pool_root_child_stats(dm_pool* pool, double* prior_dev, double* value_sum_dev, void* stream);
 /* self_play's re-rooting with subtree reuse (mcts.py:105-108); action_dev[t] < 0 leaves tree t alone */
 int dm_pool_advance(dm_pool* pool, const int32_t* action_dev, void* stream);
 /* current root states; any pointer may be NULL */
 int dm_pool_states(dm_pool* pool, uint64_t* first_dev, uint64_t* second_dev, uint8_t* player_dev,
                    uint8_t* is_final_dev, float* outcome_dev, void* stream);
-/* counters since creation (synchronises): [0] simulations, [1] leaf evaluations requested,
+/* counters since creation (synchronises).  Returns DM_ERR_CAPACITY (with out[] filled) when [8] grew since the
+ * previous call -- each capacity error is reported once, the pool stays usable: [0] simulations, [1] leaf evaluations requested,
  * [2] terminal simulations, [3] nodes allocated high-water, [4] games finished (self-play),
  * [5] sum of selection depths, [6] children scanned, [7] children created, [8] capacity errors,
- * [9] moves played (self-play), [10] rollout plies, [11] invalid actions, [12] arena compactions */
+ * [9] moves played (self-play), [10] rollout plies, [11] invalid actions, [12] arena compactions,
+ * [13] leaves served by the evaluation cache, [14] leaves aliased to an equal leaf of the same round,
+ * [15] rows inserted into the evaluation cache.  [1] counts only leaves the evaluator really ran. */
 int dm_pool_counters(dm_pool* pool, uint64_t out[16]);
 
 /* --------------------------------------------------- continuous batched self-play
@@ -214,9 +247,14 @@ int dm_selfplay_enable(dm_pool* pool, int replay_capacity_positions);
 int dm_selfplay_select(dm_pool* pool, void* stream);
 /* replay ring buffers (device, owned by the pool): positions, visit distributions
  * pi[cap][DM_MAX_ACTIONS] float, z[cap] float in [-1,1] from the mover's perspective
- * (train.py:270-282), and the number of positions written so far (monotonic). */
+ * (train.py:270-282), and the replay counter word *written_dev (monotonic): positions written so far in its low
+ * DM_REPLAY_POS_BITS bits, games written so far in the bits above (one atomic hands out both, so games
+ * are numbered in the order their positions lie in the ring). */
 int dm_selfplay_replay(dm_pool* pool, uint64_t** first_dev, uint64_t** second_dev, uint8_t** player_dev,
                        float** pi_dev, float** z_dev, uint64_t** written_dev);
+/* game_end_dev[i % DM_REPLAY_GAME_RING] = positions written up to and including game i: the trainer's window
+ * of the last N GAMES (replay_buffer_max_size, train.py:149-151) starts at game_end[games - N - 1]. */
+int dm_selfplay_games(dm_pool* pool, uint64_t** game_end_dev);
 
 /* ------------------------------------------------------------------------- net
  * ConvolutionalNet(policy_features = num_actions, grid, in_channels = 3, num_residual,
@@ -247,6 +285,11 @@ int dm_net_finalize(dm_net* net, void* stream);
 int dm_net_evaluate(dm_net* net, int precision, int n, const int32_t* count_dev, const uint64_t* first_dev,
                     const uint64_t* second_dev, const uint8_t* player_dev, float* value_dev,
                     float* probs_dev, void* stream);
+/* the same for a compacted dense batch: board i of the batch (i < *count_dev) is the state in slot index_dev[i]
+ * and its results go to value_dev[index_dev[i]] / probs_dev[index_dev[i]] (dm_pool_leaf_index) */
+int dm_net_evaluate_indexed(dm_net* net, int precision, int n, const int32_t* count_dev, const int32_t* index_dev,
+                            const uint64_t* first_dev, const uint64_t* second_dev, const uint8_t* player_dev,
+                            float* value_dev, float* probs_dev, void* stream);
 /* GameNet.forward (gamenet.py:119-120 + hex adapters): raw value_dev[n] (pre-tanh) and
  * logits_dev[n][DM_MAX_ACTIONS] */
 int dm_net_forward(dm_net* net, int precision, int n, const uint64_t* first_dev, const uint64_t* second_dev,

@@ -105,15 +105,16 @@ def train(rank, world):
     for _ in range(3):
         tr.train_step()
     # all-reduce cost alone
-    params = [p for p in net.net.parameters()]
-    for p in params:
-        p.grad = torch.zeros_like(p)
-    from deep_mcts_b200.distributed import allreduce_gradients, reduce_counters
+    from deep_mcts_b200.distributed import reduce_counters
+    bucket = net.grad_bucket          # every .grad is a view into one flat buffer: the all-reduce runs in place
+    assert bucket is not None and bucket.attached()
+    for _ in range(3):
+        bucket.allreduce()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(20):
-        n_elems = allreduce_gradients(params)
+        n_elems = bucket.allreduce()
     e1.record()
     torch.cuda.synchronize()
     allreduce_us = e0.elapsed_time(e1) * 1000 / 20

@@ -50,6 +50,37 @@ def _worker(rank, world_size, port, results):
     p.grad = g_local.clone()
     assert dd.allreduce_gradients([p]) == 3
     assert torch.allclose(p.grad, torch.full((3,), 1.5))
+
+    # GradientBucket: gradients as views into one flat buffer, all-reduced in place (no flatten copies); a
+    # training step through it keeps the replicas identical and gives the same update as the copy path
+    torch.manual_seed(7)
+    net_a = ConvolutionalOthelloNet(4, num_residual=1, channels=8, value_head_hidden_units=16)
+    net_b = net_a.copy()
+    net_b.load_state_dict(net_a.net.state_dict())
+    net_a.grad_sync = dd.allreduce_gradients
+    net_b.grad_bucket = dd.GradientBucket(net_b.net.parameters())
+    assert net_b.grad_bucket.attached() and net_b.grad_bucket.flat.numel() == sum(q.numel() for q in net_b.net.parameters())
+    for step in range(2):      # the second step checks that zero() kept the views alive
+        net_a.train(x, pi, z)
+        net_b.train(x, pi, z)
+        assert net_b.grad_bucket.attached()
+    for qa, qb in zip(net_a.net.parameters(), net_b.net.parameters()):
+        assert torch.allclose(qa, qb, atol=1e-7), "bucket path differs from the copy path"
+    sums_b = [None, None]
+    dist.all_gather_object(sums_b, [q.double().sum().item() for q in net_b.net.parameters()])
+    assert sums_b[0] == sums_b[1]
+
+    # BatchNorm running statistics drift apart (each rank normalises its own shard); the transfer averages them
+    bufs_before = [None, None]
+    dist.all_gather_object(bufs_before, [b.double().sum().item() for b in net_b.net.buffers() if b.is_floating_point()])
+    assert bufs_before[0] != bufs_before[1]
+    dd.allreduce_buffers(net_b.net)
+    bufs_after = [None, None]
+    dist.all_gather_object(bufs_after, [b.double().sum().item() for b in net_b.net.buffers() if b.is_floating_point()])
+    assert bufs_after[0] == bufs_after[1]
+    for got, a, b in zip(bufs_after[0], bufs_before[0], bufs_before[1]):
+        assert abs(got - (a + b) / 2) < 1e-5
+    dd.barrier()
     dist.destroy_process_group()
     results.put(rank)
 

@@ -332,3 +332,24 @@ def test_net_guided_search_is_exact_given_the_device_outputs(name, g, precision)
             ref.advance(int(actions[t]))
         batch.advance(actions)
     assert batch.pool.counters()["capacity_errors"] == 0
+
+
+@pytest.mark.parametrize("name", ["othello", "hex", "hex_with_swap", "tictactoe"])
+def test_reference_written_checkpoint_evaluates_on_the_device(golden_dir, name):
+    """A checkpoint written by the reference's own save_full (tests/golden/make_train_golden.py) loaded through
+    from_path_full and evaluated by the CUDA kernels: GameNet.evaluate's value and masked policy within 1e-5 of
+    what the reference computed for the same positions (gamenet.py:61-85), for single states through the public
+    ``evaluate(state)`` and for the whole batch through the device net."""
+    from test_train_cpu import load_reference_checkpoint
+    z = np.load(golden_dir / f"train_{name}.npz")
+    net = load_reference_checkpoint(golden_dir, name)
+    net.precision = "fp32"
+    m = net.manager
+    value, probs = net.evaluate_batch(z["player"], z["first"], z["second"])
+    np.testing.assert_allclose(value, z["eval_value"], atol=1e-5, rtol=0)
+    np.testing.assert_allclose(probs, z["eval_probs"], atol=1e-5, rtol=0)
+    for i in range(4):
+        state = m._make_state(int(z["player"][i]), int(z["first"][i]), int(z["second"][i]))
+        v, p = net.evaluate(state)
+        assert abs(v - z["eval_value"][i]) <= 1e-5
+        np.testing.assert_allclose(p.numpy(), z["eval_probs"][i], atol=1e-5, rtol=0)

@@ -14,16 +14,20 @@ pytestmark = pytest.mark.gpu
 from test_games_gpu import manager_for  # noqa: E402
 
 
-def evaluate_leaves(pool, game, evaluator, n):
+def evaluate_leaves(pool, game, evaluator, n, dense=False):
+    """Host evaluation of the pending leaf batch.  ``dense``: the batch is the dense one of
+    ``pool.round(selfplay=True)`` -- its n live slots are listed in ``pool.leaf_index`` and every result goes to
+    its own slot."""
     from deep_mcts_b200 import _lib
     T = pool.n_trees
     pri = np.zeros((T, _lib.DM_MAX_ACTIONS), np.float64)
     val = np.zeros(T, np.float64)
     if n:
-        p = pool.leaf_player[:n].cpu().numpy()
-        f = pool.leaf_first[:n].cpu().numpy().view(np.uint64)
-        s = pool.leaf_second[:n].cpu().numpy().view(np.uint64)
-        for i in range(n):
+        slots = pool.leaf_index[:n].cpu().numpy() if dense else np.arange(n)
+        p = pool.leaf_player.cpu().numpy()
+        f = pool.leaf_first.cpu().numpy().view(np.uint64)
+        s = pool.leaf_second.cpu().numpy().view(np.uint64)
+        for i in slots:
             v, probs = evaluator(game, (int(p[i]), int(f[i]), int(s[i])))
             val[i] = v
             pri[i, : game.num_actions] = probs
@@ -42,8 +46,9 @@ def host_round(pool, game, evaluator, carry=None):
     if "pri" not in carry:
         carry["pri"], carry["val"] = evaluate_leaves(pool, game, evaluator, 0)
     pool.round(carry["pri"], carry["val"], selfplay=True)
-    assert int(pool.leaf_count.item()) == pool.n_trees
-    carry["pri"], carry["val"] = evaluate_leaves(pool, game, evaluator, pool.n_trees)
+    n = int(pool.leaf_count.item())
+    assert 0 <= n <= pool.n_trees
+    carry["pri"], carry["val"] = evaluate_leaves(pool, game, evaluator, n, dense=True)
 
 
 @pytest.mark.parametrize("fused", [False, True])
@@ -71,7 +76,7 @@ def test_selfplay_games_match_oracle(name, g, sims, fused):
             break
     c = pool.counters()
     assert c["games"] >= T and c["capacity_errors"] == 0
-    written = int(pool.replay_written.item())
+    written = pool.positions_written()
     assert written >= T * plies
     first = pool.replay_first[:written].cpu().numpy().view(np.uint64)
     second = pool.replay_second[:written].cpu().numpy().view(np.uint64)
@@ -113,9 +118,8 @@ def test_selfplay_with_device_net_runs_and_labels_consistently():
     f2, s2, p2, pi2, z2 = engine2.sample_batch(48)
     assert pi2.shape == (48, 17) and z2.shape == (48, 1) and f2.shape == (48,)
     np.testing.assert_allclose(pi2.sum(dim=1).cpu().numpy(), 1.0, atol=1e-5)
-    # sampling restricted to what was complete at a snapshot, minus the slots about to be overwritten
-    snap = engine2.positions_written_per_pool()
-    f3, _, _, pi3, _ = engine2.sample_batch(16, written=snap, skip_oldest=8)
+    # sampling restricted to the last few GAMES (reference train.py:149-151 trims the buffer in games)
+    f3, _, _, pi3, _ = engine2.sample_batch(16, max_games=6)
     assert f3.shape == (16,) and pi3.shape == (16, 17)
 
 
@@ -143,14 +147,15 @@ def test_pipelined_pool_graph_accounting():
     # every finished move took exactly `sims` simulations; at most one move per tree is in progress
     assert c["moves"] * sims <= c["simulations"] <= (c["moves"] + 96) * sims
     for pool in engine.pools:
-        n = min(int(pool.replay_written.item()), pool.replay_capacity)
+        n = min(pool.positions_written(), pool.replay_capacity)
         pi = pool.replay_pi[:n, :17].cpu().numpy()
         np.testing.assert_allclose(pi.sum(axis=1), 1.0, atol=1e-5)
 
 
 def test_weight_transfer_keeps_graph_valid_and_changes_outputs():
-    """Re-packing weights (the reference's weight transfer, train.py:169-171) must update the kernels'
-    weights in place: outputs follow the new weights and a captured CUDA graph of the round stays valid."""
+    """Re-packing weights (the reference's weight transfer, train.py:169-171) must reach every kernel argument:
+    outputs follow the new weights on the eager path AND on the CUDA-graph replay of the self-play round (the
+    captured graph is dropped at the transfer), and the evaluation cache forgets the old network."""
     from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
     from deep_mcts_b200.selfplay import BatchedSelfPlay
     from oracle import net as onet
@@ -179,7 +184,50 @@ def test_weight_transfer_keeps_graph_valid_and_changes_outputs():
     np.testing.assert_allclose(vb, want_b[0], atol=1e-5, rtol=0)
     assert np.abs(pa - pb).max() > 1e-3
     before = engine.counters()["simulations"]
-    engine.run_rounds(30)          # replays the graph captured before the transfer
+    engine.run_rounds(30)          # the round graph is re-captured: it froze the old biases and value-head weights
     torch.cuda.synchronize()
     c = engine.counters()
     assert c["simulations"] > before and c["capacity_errors"] == 0
+    # the outputs the REPLAYED round left pending must come from the new weights (by-value kernel arguments
+    # included), for every leaf the round evaluated
+    pool = engine.pool
+    n = int(pool.leaf_count.item())
+    assert n > 0
+    slots = pool.leaf_index[:n].cpu().numpy()
+    lp = pool.leaf_player.cpu().numpy()[slots]
+    lf = pool.leaf_first.cpu().numpy().view(np.uint64)[slots]
+    ls = pool.leaf_second.cpu().numpy().view(np.uint64)[slots]
+    want_v, want_p = onet.evaluate_batch(game, sd_b, [(int(a), int(b), int(c2)) for a, b, c2 in zip(lp, lf, ls)])
+    got_p = dn._probs[torch.from_numpy(slots).long().to(pool.device)][:, : game.num_actions].cpu().numpy()
+    got_v = dn._value[torch.from_numpy(slots).long().to(pool.device)].cpu().numpy()
+    np.testing.assert_allclose(got_p, want_p, atol=1e-5, rtol=0)
+    np.testing.assert_allclose(got_v, want_v, atol=1e-5, rtol=0)
+
+
+def test_replay_window_in_games():
+    """The replay ring numbers games in ring order (one atomic hands out positions and game number): the window of
+    the last N games starts where game (games - N) starts, and a sample restricted to it only returns positions
+    of those games (reference train.py:149-151)."""
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200.pool import TreePool
+    from deep_mcts_b200.selfplay import BatchedSelfPlay
+    manager = manager_for("tictactoe", 3)
+    pool = TreePool(manager, 64, 1 << 12, seed=2)
+    pool.configure(6, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, 3, 0.5, 0.25)
+    pool.enable_selfplay(1 << 15)
+    game = make_game("tictactoe", 3)
+    carry = {}
+    for _ in range(260):
+        host_round(pool, game, oev.uniform, carry)
+    positions, games = pool.replay_progress()
+    assert games == pool.counters()["games"] and games > 100 and positions <= pool.replay_capacity
+    ends = pool.replay_game_end[:games].cpu().numpy()
+    assert (np.diff(ends) >= 5).all() and (np.diff(ends) <= 9).all() and ends[-1] == positions   # 5..9 plies per game
+    start = pool.replay_window_start(10)
+    assert start == ends[games - 11]
+    # positions of one game are contiguous and start at ply 0: an empty board with FIRST to move
+    first = pool.replay_first[:positions].cpu().numpy()
+    second = pool.replay_second[:positions].cpu().numpy()
+    starts = np.concatenate([[0], ends[:-1]])
+    assert (first[starts] == 0).all() and (second[starts] == 0).all()
+    assert pool.replay_window_start(10 ** 6) == 0
