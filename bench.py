@@ -3,9 +3,9 @@
 
     python bench.py --gpus N --steps K --warmup W [--impl b200|reference] [--workload othello8|hex7]
 
-One "step" = ``num_simulations`` (50) search rounds over the whole pool: every round selects one
-leaf per tree (PUCT descent, terminal leaves handled in place), evaluates the batch with the
-conv policy/value net and expands + backs up.  Workload at N=1: Othello 8x8 self-play, 4096
+One "step" = 10 moves of every game = 10 x ``num_simulations`` (500) search rounds over the whole pool: every
+round selects one leaf per tree (PUCT descent, terminal leaves handled in place), evaluates the leaves the
+device evaluation cache does not know with the conv policy/value net and expands + backs up.  Workload at N=1: Othello 8x8 self-play, 4096
 concurrent games, ConvolutionalOthelloNet(8) random-init weights, 50 sims/move, cutoff 10,
 Dirichlet alpha 1.0 (BASELINE.json configs[2] at one GPU; --workload hex7 runs configs[1]).
 Games shard across GPUs with no collective on the search path (weak scaling).
@@ -31,12 +31,13 @@ WORKLOADS = {
 }
 METRIC = "mcts_simulations_per_sec"
 UNIT = "sims/s"
+MOVES_PER_STEP = 10   # one step = 10 moves of every game = 10 x num_simulations search rounds over the pool
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="othello8", choices=sorted(WORKLOADS))
@@ -44,10 +45,14 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample per process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--profile-steps", type=int, default=2, help="steps of the per-kernel CUDA-event pass")
     ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
     ap.add_argument("--pool-sizes", type=str, default="", help="comma-separated games per pool (default: even split)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay a captured CUDA graph of the round")
+    ap.add_argument("--ncu-rounds", type=int, default=0,
+                    help="profiling aid: after the warm-up run this many rounds launch by launch inside a "
+                         "cudaProfilerStart/Stop range (ncu --profile-from-start off) and exit")
     ap.add_argument("--cache-log2", type=int, default=22,
                     help="log2 entries of the device evaluation cache (reference train.py:408-414); 0 = off")
     return ap.parse_args()
@@ -108,7 +113,9 @@ def config_block(args, wl, n_gpus):
                     f"Convolutional{wl['game'].title().replace('_', '')}Net({wl['grid']}) C=128 R=3 random-init, "
                     f"{wl['num_simulations']} sims/move, cutoff {wl['sample_move_cutoff']}, "
                     f"dirichlet {wl['dirichlet_alpha']}",
-        "step": f"{wl['num_simulations']} search rounds over the pool (one leaf per tree per round)",
+        "step": f"{MOVES_PER_STEP} moves of every game = {MOVES_PER_STEP * wl['num_simulations']} search rounds over the pool "
+                "(one simulation per tree per round)",
+        "eval_cache": f"device evaluation cache 2^{args.cache_log2} entries (reference train.py:408-414)" if args.cache_log2 > 0 else "off",
         "trees_per_gpu": args.trees, "pools_per_gpu": args.pools, "cuda_graph": bool(args.graph),
         "num_simulations": wl["num_simulations"],
         "parallelism": f"games sharded x{n_gpus}",
@@ -205,6 +212,30 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------- b200 arm
+class EnergyMeter:
+    """Board energy from NVML's total-energy counter (millijoules since driver load) around a region."""
+
+    def __init__(self, index):
+        self.handle = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.read()
+        except Exception:
+            self.handle = None
+
+    def read(self):
+        if self.handle is None:
+            return None
+        try:
+            return self.nvml.nvmlDeviceGetTotalEnergyConsumption(self.handle) / 1000.0
+        except Exception:
+            self.handle = None
+            return None
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -219,6 +250,8 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     from deep_mcts_b200 import _lib
+    from deep_mcts_b200.gamenet import cached_state_evaluator
+    from deep_mcts_b200.mcts import BatchedMCTS
     from deep_mcts_b200.selfplay import BatchedSelfPlay
 
     wl = workload_config(args)
@@ -232,12 +265,12 @@ def run_b200(args):
     net.precision = args.precision
     net.max_batch = args.trees
     sims, T = wl["num_simulations"], args.trees
+    rounds_per_step = MOVES_PER_STEP * sims
     engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
                              replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools,
                              pool_sizes=[int(x) for x in args.pool_sizes.split(",")] if args.pool_sizes else None,
                              eval_cache_log2=args.cache_log2 if args.cache_log2 > 0 else None)
     engine.use_graph = bool(args.graph)
-    dn = net.device_net()   # e2e leg (full-width batches)
     lib = _lib.load()
 
     def barrier():
@@ -245,23 +278,37 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also desynchronises the games' phases; captures the round graph when enabled)
+    # ---- warm-up: W steps of 10 moves each play most of a first game, so the timed region sees games at every
+    # stage (and the round graph is captured)
     clocks = ClockSampler(local_rank)
+    energy = EnergyMeter(local_rank)
     if rank == 0:
         clocks.start()
     for _ in range(args.warmup):
-        engine.run_rounds(sims)
+        engine.run_rounds(rounds_per_step)
     barrier()
+    if args.ncu_rounds > 0:
+        engine.use_graph = False
+        engine.run_rounds(2)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        engine.run_rounds(args.ncu_rounds)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"ncu_rounds": args.ncu_rounds, "note": "profiling run, no measurement"}))
+        return
     c0 = engine.counters()
     launches0 = lib.dm_launch_count() + engine.graph_launches()
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     clocks.mark()
+    j0 = energy.read()
     start.record()
     for _ in range(args.steps):
-        engine.run_rounds(sims)
+        engine.run_rounds(rounds_per_step)
     stop.record()
     barrier()
+    j1 = energy.read()
     elapsed_ms = start.elapsed_time(stop)
     clock_info = clocks.stop() if rank == 0 else None
     launches = lib.dm_launch_count() + engine.graph_launches() - launches0
@@ -278,10 +325,10 @@ def run_b200(args):
     p0 = engine.counters()
     engine.tree_timers = [] if args.pools == 1 else None
     pstart, pstop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    prof_steps = min(args.steps, 3)
+    prof_steps = max(1, min(args.steps, args.profile_steps))
     pstart.record()
     for _ in range(prof_steps):
-        engine.run_rounds(sims)
+        engine.run_rounds(rounds_per_step)
     pstop.record()
     torch.cuda.synchronize()
     prof_elapsed_ms = pstart.elapsed_time(pstop)
@@ -299,66 +346,56 @@ def run_b200(args):
     prof_leaf_evals = p1["leaf_evals"] - p0["leaf_evals"]
     engine.use_graph = was_graph
 
-    # ---- end to end through the public batched API with HOST buffers (pinned), fresh roots per step
-    from deep_mcts_b200.pool import TreePool, default_node_capacity
+    # ---- end to end through the public API with HOST buffers: host-driven self-play.  Every step is one move of T
+    # games played the way the reference's MCTS.self_play does it (mcts.py:96-111), batched: the games start from
+    # mid-game states uploaded from pinned HOST memory; step() runs the simulations with the reference's cached
+    # evaluator (cached_state_evaluator(net), train.py:408-414) and returns visit counts and statistics as host
+    # arrays, the host picks the moves (argmax) into a pinned buffer, advance() copies them in and re-roots every
+    # tree with subtree reuse, states() brings the successor states back to the host, finished games are reset.
     parts = [pl.states() for pl in engine.pools]
     p, f, s, fin = (np.concatenate([part[i] for part in parts]) for i in range(4))
-    keep = ~fin
-    idx = np.where(keep)[0]
-    idx = np.resize(idx, T)
+    idx = np.resize(np.where(~fin)[0], T)
     h_first = torch.from_numpy(f[idx].view(np.int64).copy()).pin_memory()
     h_second = torch.from_numpy(s[idx].view(np.int64).copy()).pin_memory()
     h_player = torch.from_numpy(p[idx].copy()).pin_memory()
-    h_visits = torch.empty((T, _lib.DM_MAX_ACTIONS), dtype=torch.int32).pin_memory()
-    h_stats = torch.empty((T, 2), dtype=torch.int32).pin_memory()
-    pool2 = TreePool(net.manager, T, 4096, seed=7)
-    pool2.configure(sims, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, 0, 0.0, 0.25)
-    d_first = torch.empty(T, dtype=torch.int64, device="cuda")
-    d_second = torch.empty(T, dtype=torch.int64, device="cuda")
-    d_player = torch.empty(T, dtype=torch.uint8, device="cuda")
-    stream = torch.cuda.current_stream().cuda_stream
-
-    e2e_graph = None
-    if args.graph:
-        pool2.begin_step()
-        dn.run_search(pool2, 1)
-        torch.cuda.synchronize()
-        e2e_launches_before = lib.dm_launch_count()
-        e2e_graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(e2e_graph):
-            dn.search_round(pool2, fused=True)
-        e2e_round_launches = int(lib.dm_launch_count() - e2e_launches_before)
+    searcher = BatchedMCTS(net.manager, T, sims, None, cached_state_evaluator(net), seed=7,
+                           dirichlet_alpha=wl["dirichlet_alpha"], dirichlet_factor=wl["dirichlet_factor"])
+    searcher.pool.set_root_states(h_player.numpy(), h_first.numpy().view(np.uint64), h_second.numpy().view(np.uint64))
+    h_actions = torch.zeros(T, dtype=torch.int32).pin_memory()
 
     def e2e_step():
-        d_first.copy_(h_first, non_blocking=True)
-        d_second.copy_(h_second, non_blocking=True)
-        d_player.copy_(h_player, non_blocking=True)
-        _lib.call("dm_pool_set_root_state", pool2._h, 0, T, d_first.data_ptr(), d_second.data_ptr(),
-                  d_player.data_ptr(), stream)
-        pool2.begin_step()
-        dn.run_search(pool2, sims, round_graph=e2e_graph)
-        _lib.call("dm_pool_root_visits", pool2._h, pool2._visits.data_ptr(), pool2._stats.data_ptr(), stream)
-        h_visits.copy_(pool2._visits, non_blocking=True)
-        h_stats.copy_(pool2._stats, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        pool = searcher.pool
+        visits, stats = searcher.step()                           # D2H: visit counts + statistics
+        h_actions.numpy()[:] = visits.argmax(axis=1)              # the host chooses the moves (mcts.py:99-104)
+        searcher.advance(h_actions.numpy())                       # H2D: chosen actions; re-root with subtree reuse
+        np_p, np_f, np_s, np_fin, _ = pool.states()               # D2H: successor states, final flags
+        if np_fin.any():
+            pool.reset(np.where(np_fin)[0].astype(np.int32))      # H2D: finished games start over
+        return int(stats.sum())
 
-    e2e_step()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.e2e_steps):
+    for _ in range(3):
         e2e_step()
+    barrier()
+    ce0 = searcher.pool.counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_launch0 = lib.dm_launch_count()
+    e0.record()
+    e2e_sims = 0
+    for _ in range(args.e2e_steps):
+        e2e_sims += e2e_step()
     e1.record()
     barrier()
     e2e_ms = e0.elapsed_time(e1)
-    e2e_sims = int(h_stats.sum().item()) * args.e2e_steps  # every step repeats the same work
-    h2d = T * 17
-    d2h = T * (_lib.DM_MAX_ACTIONS * 4 + 8)
+    h2d = T * 4                                              # chosen actions (+ the ids of finished games)
+    d2h = T * (net.manager.num_actions * 4 + 8 + 17 + 5)     # visit counts + stats, successor states + final flag/outcome
+    ce1 = searcher.pool.counters()
+    ce = {k: ce1[k] - ce0[k] for k in ce1}
 
     # ---- reduce over ranks: sums of work, max of time
     from deep_mcts_b200.distributed import reduce_counters
+    joules = (j1 - j0) if (j0 is not None and j1 is not None) else 0.0
     sums, maxima = reduce_counters(
-        {"sims": d["simulations"], "evals": d["leaf_evals"], "e2e_sims": e2e_sims, "launches": launches},
+        {"sims": d["simulations"], "evals": d["leaf_evals"], "e2e_sims": e2e_sims, "launches": launches, "joules": joules},
         {"elapsed_ms": elapsed_ms, "e2e_ms": e2e_ms}, "cuda")
     tot_sims, tot_evals, tot_e2e_sims, tot_launches = sums["sims"], sums["evals"], sums["e2e_sims"], sums["launches"]
     elapsed_ms, e2e_ms = maxima["elapsed_ms"], maxima["e2e_ms"]
@@ -368,15 +405,21 @@ def run_b200(args):
         flop_per_leaf_conv = 2.0 * g * g * 9 * 128 * 128  # 18.87 MFLOP at g=8, 14.45 at g=7
         conv_ms, conv_launches = prof["trunk_conv"]
         peaks = {}
+        burst, sustained = 1590.0, 1590.0
         peak_src = "fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, 6.65 TB/s)"
-        peak_tflops = 1590.0
         try:
             peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
-            peak_tflops = float(peaks["bf16_tflops_sustained"])
-            peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+            burst, sustained = float(peaks["bf16_tflops"]), float(peaks["bf16_tflops_sustained"])
+            peak_src = "MEASURED_PEAKS.json"
         except Exception:
             peaks = {}
+        # the kernel is timed inside a loop that has kept the GPU busy for load_s seconds: sustained figure from 2 s on
+        load_s = (elapsed_ms + prof_elapsed_ms) * 1e-3
+        use_sustained = load_s >= 2.0
+        peak_tflops = sustained if use_sustained else burst
         achieved = (prof_leaf_evals * 7 * flop_per_leaf_conv) / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        tree = tree_roofline(pd, tree_ms, peaks)
+        total_j = sums["joules"]
         line = {
             "metric": METRIC, "value": tot_sims / (elapsed_ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -385,37 +428,53 @@ def run_b200(args):
             "config": config_block(args, wl, world),
             "leaf_evals_per_sec": tot_evals / (elapsed_ms * 1e-3),
             "e2e": {"value": tot_e2e_sims / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h,
-                    "what": "batched MCTS.step through the public API: root states from pinned host memory, "
-                            f"{sims} sims + root expansion per tree, visit counts back to pinned host memory"},
+                    "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                    "leaf_evals_per_step": ce["leaf_evals"] / max(1, args.e2e_steps),
+                    "cache_served_fraction": (ce["cache_hits"] + ce["cache_aliases"]) /
+                                             max(1, ce["cache_hits"] + ce["cache_aliases"] + ce["leaf_evals"]),
+                    "gpu_launches_direct": int(lib.dm_launch_count() - e2e_launch0),
+                    "what": "host-driven self-play through the public batched MCTS API, one move of every game per step "
+                            f"(the reference's MCTS.self_play loop, mcts.py:96-111): BatchedMCTS.step(): {sims} simulations "
+                            "per tree with cached_state_evaluator(net), visit counts + statistics to host arrays (D2H) -> "
+                            "host argmax into pinned memory -> advance(actions) (H2D, re-root with subtree reuse) -> "
+                            "states() (D2H); finished games restart"},
             "gpu_launches": int(tot_launches),
             "clocks": clock_info,
+            "energy": {"joules_per_step": total_j / args.steps if total_j else None,
+                       "joules_per_million_sims": total_j / (tot_sims / 1e6) if total_j else None,
+                       "joules_per_tflop_useful": total_j / (tot_evals * 7 * flop_per_leaf_conv / 1e12) if total_j and tot_evals else None,
+                       "mean_watts_per_gpu": total_j / world / (elapsed_ms * 1e-3) if total_j else None,
+                       "source": "NVML total energy counter around the timed region"},
             "roofline": {
                 "kernel": "k_resblock_tc<G> x1 + k_conv3x3_tc2 x1 per round (tcgen05 implicit-GEMM 3x3 convs: the three fused "
                           "residual blocks in one launch and the policy conv; seven 128->128 convolutions in two launches)",
                 "bound": "tensor", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s",
                 "frac": achieved / peak_tflops if peak_tflops else None,
+                "frac_of_burst": achieved / burst, "frac_of_sustained": achieved / sustained,
                 "traffic": ncu_dram_traffic_per_launch() if wl["game"] == "othello" and args.trees == 4096 else None,
-                "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch = three residual blocks (ncu --set full, "
-                                "profiles/r1g_round_kernels_ncu_full_raw.csv; the blocks' intermediate activations "
-                                "are re-read from the 126 MB L2)",
+                "traffic_unit": "DRAM bytes per k_resblock_tc<8> launch = three residual blocks (ncu --set full capture "
+                                "under profiles/; the blocks' intermediate activations are re-read from the 126 MB L2)",
                 # per fused residual block: the block input is read once (it is also the skip operand) and the
                 # output written once, 128 bf16 channels per cell, plus two 9x128x128 bf16 weight sets; a launch
-                # runs the trunk's three blocks
-                "algorithmic_bytes_per_launch": 3 * (2 * args.trees * g * g * 256 + 2 * 9 * 128 * 128 * 2),
-                "peak_source": peak_src, "launches": conv_launches,
+                # runs the trunk's three blocks over the leaves the evaluation cache did not serve
+                "algorithmic_bytes_per_launch": 3 * (2 * (prof_leaf_evals / max(1, prof_steps * rounds_per_step)) * g * g * 256
+                                                     + 2 * 9 * 128 * 128 * 2),
+                "peak_source": f"{peak_src} bf16_tflops{'_sustained' if use_sustained else ''}: the kernels are timed after "
+                               f"{load_s:.1f} s of continuous load (burst below 2 s, sustained from 2 s on)",
+                "launches": conv_launches,
                 "avg_launch_ms": conv_ms / conv_launches if conv_launches else None,
                 "algorithmic_flop_per_launch": prof_leaf_evals * 7 * flop_per_leaf_conv / max(1, conv_launches),
                 "share_of_step": conv_ms / prof_elapsed_ms if prof_elapsed_ms else None,
-                "timed_in": f"{prof_steps} extra steps launched kernel by kernel right after the timed region "
-                            "(CUDA events cannot be timed inside the replayed graph)",
+                "timed_in": f"{prof_steps} extra steps ({prof_steps * rounds_per_step} rounds) launched kernel by kernel right "
+                            "after the timed region (CUDA events cannot be timed inside the replayed graph)",
+                # second entry: the tree kernel (one launch per round), HBM-bound by construction
+                "tree": tree,
             },
             "eval_cache": {"log2_entries": args.cache_log2, "hits": d["cache_hits"], "aliases": d["cache_aliases"],
                            "inserts": d["cache_inserts"], "leaf_evals": d["leaf_evals"],
                            "served_fraction": (d["cache_hits"] + d["cache_aliases"]) /
                                               max(1, d["cache_hits"] + d["cache_aliases"] + d["leaf_evals"])},
             "kernel_ms": {**{k: v[0] for k, v in prof.items()}, **tree_ms},
-            "tree_roofline": tree_roofline(pd, tree_ms, peaks),
             "tree_stats": {"mean_depth": d["depth_sum"] / max(1, d["simulations"]),
                            "children_scanned_per_sim": d["children_scanned"] / max(1, d["simulations"]),
                            "terminal_fraction": d["terminal_sims"] / max(1, d["simulations"]),
@@ -426,13 +485,18 @@ def run_b200(args):
             from oracle import cpu_selfplay  # noqa: cpu_baseline leg only
             procs = cpu_selfplay.default_procs()
             res = cpu_selfplay.run(wl, procs, 1, args.cpu_seconds)
-            cs, ce, cw = res[0]
+            cs, ce_, cw = res[0]
+            # BASELINE.md section 3 asks for the one-process figure next to the all-cores one
+            one = cpu_selfplay.run({**wl, "torch_threads": procs}, 1, 1, args.cpu_seconds)[0]
             line["cpu_baseline"] = {
                 "value": cs / cw, "unit": UNIT, "cores": procs, "kind": "port",
-                "leaf_evals_per_sec": ce / cw,
+                "leaf_evals_per_sec": ce_ / cw,
                 "sample": f"{procs} processes x 1 torch thread x {args.cpu_seconds:.0f} s of full self-play games "
                           "with the same net/config (oracle port of the reference loop; the Python reference "
                           "itself is not present on the GPU box)",
+                "single_process": {"value": one[0] / one[2], "unit": UNIT, "torch_threads": procs,
+                                   "leaf_evals_per_sec": one[1] / one[2],
+                                   "sample": f"1 process, torch intra-op threads = {procs}, {args.cpu_seconds:.0f} s"},
                 "calibration": "in the build container the port runs 1.19x faster per process than the unmodified "
                                "reference (331 vs 278 sims/s), see DESIGN.md section 6"}
         print(json.dumps(line))

@@ -100,7 +100,9 @@ struct PoolView {
     u32* cmark;     // [n_trees][cap_words]
     u32* cprefix;   // [n_trees][cap_words]
     u32 cap_words;
-    unsigned long long* counters;
+    unsigned long long* counters;   // [16] global counters (kernels outside the hot loop add here atomically)
+    unsigned long long* tcount;     // [n_trees][16] per-tree counter rows: the hot kernels add here without atomics
+    u32* scnt;                      // this warp's shared-memory accumulator (set inside the hot kernels), else null
     // evaluation cache (cctl == null: disabled)
     unsigned long long* cctl;   // [centries]
     u64* ckey_first;            // [centries]
@@ -131,10 +133,34 @@ struct PoolView {
 };
 
 // ------------------------------------------------------------------ small warp helpers
+// Counters.  The hot kernels (one warp per tree, thousands of trees) accumulate in a per-warp shared-memory row and
+// add it to the tree's own row of tcount once per launch: ~10 atomics per tree per round on ONE cache line become
+// one coalesced read-modify-write of a line nobody else touches.  Everything else adds to the global row atomically.
+// Called by one lane of the warp only.
 __device__ __forceinline__ void count(const PoolView& P, int which, unsigned long long v) {
 #ifndef DM_EXP_NOCOUNT   // timing experiment: how much of the tree kernels is the shared counters
-    if (v) atomicAdd(&P.counters[which], v);
+    if (P.scnt) P.scnt[which] += (u32)v;
+    else if (v) atomicAdd(&P.counters[which], v);
 #endif
+}
+__device__ __forceinline__ void count_nodes_high(const PoolView& P, u32 nodes) {
+    if (P.scnt) P.scnt[kCntNodesHigh] = max(P.scnt[kCntNodesHigh], nodes);
+    else atomicMax(&P.counters[kCntNodesHigh], (unsigned long long)nodes);
+}
+// whole warp: clear / flush this warp's accumulator row
+__device__ __forceinline__ void counters_begin(u32* row, int lane) {
+    if (lane < 16) row[lane] = 0;
+    __syncwarp();
+}
+__device__ __forceinline__ void counters_flush(const PoolView& P, int t, const u32* row, int lane) {
+    __syncwarp();
+    if (lane < 16) {
+        const u32 v = row[lane];
+        if (v) {
+            unsigned long long* dst = P.tcount + (size_t)t * 16 + lane;
+            *dst = (lane == kCntNodesHigh) ? max(*dst, (unsigned long long)v) : *dst + v;
+        }
+    }
 }
 
 __device__ __forceinline__ GState root_state(const PoolView& P, int t) {
@@ -335,18 +361,42 @@ __device__ __forceinline__ void round_end(const PoolView& P, bool dense) {
     __threadfence();
     if (threadIdx.x == 0) P.cround[0] = (P.cround[0] + 1) & kStampMask;
     if (!dense) return;
+    // every thread takes 32 consecutive trees per pass: one 32-byte load of their flags (no dependent-load chain in
+    // this serial tail of the launch), a bit mask, one block-wide exclusive scan of the counts
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nthreads = kWarpsPerBlock * 32;
     u32 running = 0;
-    for (int base = 0; base < P.n_trees; base += nthreads) {
-        const int t = base + (int)threadIdx.x;
-        const bool live = t < P.n_trees && __ldcv(P.leaf_live + t) != 0;
-        const u32 bal = __ballot_sync(DM_FULL_MASK, live);
-        if (lane == 0) s_warp_sums[warp] = __popc(bal);
+    for (int base = 0; base < P.n_trees; base += nthreads * 32) {
+        const int t0 = base + (int)threadIdx.x * 32;
+        u32 mask = 0;
+        if (t0 + 32 <= P.n_trees) {
+            const uint4* src = reinterpret_cast<const uint4*>(P.leaf_live + t0);
+            const uint4 a = __ldcv(src), b = __ldcv(src + 1);
+            const u32 w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    if ((w[k] >> (8 * j)) & 0xffu) mask |= 1u << (4 * k + j);
+        } else {
+            for (int j = 0; j < 32 && t0 + j < P.n_trees; ++j)
+                if (__ldcv(P.leaf_live + t0 + j)) mask |= 1u << j;
+        }
+        const u32 cnt = __popc(mask);
+        u32 incl = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const u32 up = __shfl_up_sync(DM_FULL_MASK, incl, off);
+            if (lane >= off) incl += up;
+        }
+        if (lane == 31) s_warp_sums[warp] = incl;
         __syncthreads();
-        u32 before = running;
-        for (int w = 0; w < warp; ++w) before += s_warp_sums[w];
-        if (live) P.leaf_index[before + __popc(bal & ((1u << lane) - 1u))] = t;
-        for (int w = 0; w < kWarpsPerBlock; ++w) running += s_warp_sums[w];
+        u32 pos = running + incl - cnt;
+        for (int w2 = 0; w2 < warp; ++w2) pos += s_warp_sums[w2];
+        while (mask) {
+            P.leaf_index[pos++] = t0 + __ffs(mask) - 1;
+            mask &= mask - 1;
+        }
+        for (int w2 = 0; w2 < kWarpsPerBlock; ++w2) running += s_warp_sums[w2];
         __syncthreads();
     }
     if (threadIdx.x == 0) *P.leaf_count = (int)running;
@@ -508,7 +558,7 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
         P.n_children[base + node] = (u8)n;
         P.node_count[t] = cnt + (u32)n;
         count(P, kCntCreated, (unsigned long long)n);
-        atomicMax(&P.counters[kCntNodesHigh], (unsigned long long)(cnt + n));
+        count_nodes_high(P, cnt + (u32)n);
     }
     __syncwarp();
     return true;
@@ -1145,12 +1195,19 @@ __device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, 
 }
 
 template <bool kSelfPlay>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView P) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 7) k_select(PoolView Pin) {
     __shared__ u32 s_path[kWarpsPerBlock][DM_MAX_DEPTH];
+    __shared__ u32 s_cnt[kWarpsPerBlock][16];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
+    PoolView P = Pin;
+    P.scnt = s_cnt[warp];
     const u32 now = __ldcv(P.cround);
-    if (t < P.n_trees) select_tree<kSelfPlay>(P, t, lane, s_path[warp], now);
+    if (t < P.n_trees) {
+        counters_begin(P.scnt, lane);
+        select_tree<kSelfPlay>(P, t, lane, s_path[warp], now);
+        counters_flush(P, t, P.scnt, lane);
+    }
     round_end(P, false);
 }
 
@@ -1215,11 +1272,15 @@ __device__ __forceinline__ void expand_backup_tree(const PoolView& P, int t, int
 
 template <typename PriorT>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-    k_expand_backup(PoolView P, const PriorT* priors, int stride, const PriorT* values) {
+    k_expand_backup(PoolView Pin, const PriorT* priors, int stride, const PriorT* values) {
     __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
+    __shared__ u32 s_cnt[kWarpsPerBlock][16];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
-    if (t >= P.n_trees || P.path_len[t] <= 0) return;
+    if (t >= Pin.n_trees || Pin.path_len[t] <= 0) return;
+    PoolView P = Pin;
+    P.scnt = s_cnt[warp];
+    counters_begin(P.scnt, lane);
     // the per-tree copy of the pending leaf: a leaf served by the evaluation cache or aliased to another tree's
     // slot has no slot of its own in the batch
     GState s;
@@ -1227,6 +1288,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32)
     s.second = P.pend_second[t];
     s.player = P.pend_player[t];
     expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
+    counters_flush(P, t, P.scnt, lane);
 }
 
 // One launch per search round: expand + back up the tree's pending leaf with the evaluator's output,
@@ -1242,10 +1304,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
     __shared__ u8 s_order[kWarpsPerBlock][DM_MAX_ACTIONS + 3];
     PoolView P = Pin;
     if (GAME >= 0) P.cfg = const_game_cfg<(GAME >= 0 ? GAME : 0), (G > 0 ? G : 8)>();
+    __shared__ u32 s_cnt[kWarpsPerBlock][16];
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int t = blockIdx.x * kWarpsPerBlock + warp;
+    P.scnt = s_cnt[warp];
     const u32 now = __ldcv(P.cround);
     if (t < P.n_trees) {
+        counters_begin(P.scnt, lane);
         if (P.path_len[t] > 0) {
             GState s;
             s.first = P.pend_first[t];
@@ -1254,6 +1319,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
             expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
         }
         select_tree<kSelfPlay, kSelfPlay>(P, t, lane, s_path[warp], now);
+        counters_flush(P, t, P.scnt, lane);
     }
     round_end(P, kSelfPlay);   // dense leaf batch (self-play): the last block compacts the live slots
 }
@@ -1563,6 +1629,25 @@ __global__ void k_advance(PoolView P, const int* actions) {
     compact_tree(P, t, lane);
 }
 
+// counters read-out: global row + the per-tree rows (sum; high-water mark: max) -> out[16]
+__global__ void k_sum_counters(PoolView P, unsigned long long* out) {
+    __shared__ unsigned long long s_part[32][16];
+    const int col = threadIdx.x & 15, grp = threadIdx.x >> 4;   // 512 threads = 32 groups of 16 columns
+    unsigned long long acc = 0;
+    for (int t = grp; t < P.n_trees; t += 32) {
+        const unsigned long long v = P.tcount[(size_t)t * 16 + col];
+        acc = (col == kCntNodesHigh) ? max(acc, v) : acc + v;
+    }
+    s_part[grp][col] = acc;
+    __syncthreads();
+    if (threadIdx.x < 16) {
+        unsigned long long total = P.counters[col];
+        for (int g2 = 0; g2 < 32; ++g2)
+            total = (col == kCntNodesHigh) ? max(total, s_part[g2][col]) : total + s_part[g2][col];
+        out[col] = total;
+    }
+}
+
 __global__ void k_states(PoolView P, u64* first, u64* second, u8* player, u8* is_final, float* outcome) {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= P.n_trees) return;
@@ -1656,7 +1741,8 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
         (rc = pool_alloc(p, &v.pend_flags, T)) ||
         (rc = pool_alloc(p, &v.vl_len, T * DM_MAX_LEAVES)) || (rc = pool_alloc(p, &v.vl_slot, T * DM_MAX_LEAVES)) ||
         (rc = pool_alloc(p, &v.vl_count, T)) || (rc = pool_alloc(p, &v.armed, 1)) ||
-        (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 16)) ||
+        (rc = pool_alloc(p, &v.leaf_count, 1)) || (rc = pool_alloc(p, &v.counters, 32)) ||
+        (rc = pool_alloc(p, &v.tcount, T * 16)) ||
         (rc = pool_alloc(p, &v.cround, 2)) || (rc = pool_alloc(p, &v.leaf_live, T)) ||
         (rc = pool_alloc(p, &v.leaf_index, T)))
         return fail(rc);
@@ -1983,7 +2069,9 @@ extern "C" int dm_pool_counters(dm_pool* p, uint64_t out[16]) {
     DM_CHECK_ARG(p && out, "dm_pool_counters: null argument");
     DM_CUDA(cudaSetDevice(p->cfg.device));
     DM_CUDA(cudaDeviceSynchronize());
-    DM_CUDA(cudaMemcpy(out, p->v.counters, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    k_sum_counters<<<1, 512>>>(p->v, p->v.counters + 16);
+    DM_LAUNCH_CHECK();
+    DM_CUDA(cudaMemcpy(out, p->v.counters + 16, 16 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     if (out[kCntCapacity] > p->capacity_errors_reported) {
         // reported once per new error: the counter itself stays in out[8], later calls succeed again
         p->capacity_errors_reported = out[kCntCapacity];

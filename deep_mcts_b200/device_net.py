@@ -8,6 +8,8 @@ CUDA-core path (1e-5 parity), "bf16" the tcgen05 tensor-core path (1e-2 parity, 
 """
 from typing import Dict, Optional, Tuple
 
+import weakref
+
 import numpy as np
 import torch
 
@@ -38,6 +40,9 @@ class DeviceNet:
         self._h = handle
         self._loaded = False
         self.weights_version = 0     # bumped by load_state_dict: evaluation caches of older weights are stale
+        self.graph_rounds = True     # run_search replays a captured graph of the fused round for large pools
+        self.graph_min_trees = 256
+        self._graphs = {}
         A = _lib.DM_MAX_ACTIONS
         # outputs of the search path: a fused round leaves its last batch pending here until the next round
         self._value = torch.zeros(self.max_batch, dtype=torch.float32, device=self.device)
@@ -212,6 +217,23 @@ class DeviceNet:
             timers.append(("select", ev[0], ev[1]))
             timers.append(("expand_backup", ev[2], ev[3]))
 
+    def _round_graph(self, pool):
+        """The fused search round of ``pool`` as a CUDA graph (memset + tree kernel + network kernels: a launch-bound
+        loop of ~8 small launches per round), captured on first use and again after every weight load -- the
+        trunk kernels take folded biases by value, which a capture freezes."""
+        key = id(pool)
+        hit = self._graphs.get(key)
+        if hit is not None and hit[0] == self.weights_version and hit[2]() is pool:
+            return hit[1]
+        self.search_round(pool, fused=True)     # warm every kernel outside the capture (a real round: harmless,
+        torch.cuda.synchronize(self.device)     # run_search's caller counts simulations, not rounds)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.search_round(pool, fused=True)
+        self._graphs = {k: v for k, v in self._graphs.items() if v[2]() is not None}   # drop graphs of dead pools
+        self._graphs[key] = (self.weights_version, graph, weakref.ref(pool))
+        return graph
+
     def evaluate_pending(self, pool) -> None:
         """Network evaluation + expand/backup of the leaves a previous select left pending."""
         if pool.dense_batch:
@@ -231,6 +253,8 @@ class DeviceNet:
             # last batch's expand/backup
             pool.select()
             self.evaluate_device(pool.leaf_first, pool.leaf_second, pool.leaf_player, pool.leaf_capacity, pool.leaf_count)
+            if round_graph is None and self.graph_rounds and pool.n_trees >= self.graph_min_trees and int(sims) >= 8:
+                round_graph = self._round_graph(pool)
             for _ in range(int(sims)):
                 if round_graph is not None:
                     round_graph.replay()
