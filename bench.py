@@ -45,7 +45,7 @@ def parse_args():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU baseline sample per process")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=20)
+    ap.add_argument("--e2e-steps", type=int, default=60, help="moves per game of the end-to-end leg (60 = about one whole game per tree)")
     ap.add_argument("--profile-steps", type=int, default=2, help="steps of the per-kernel CUDA-event pass")
     ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
     ap.add_argument("--pool-sizes", type=str, default="", help="comma-separated games per pool (default: even split)")
@@ -362,15 +362,28 @@ def run_b200(args):
                            dirichlet_alpha=wl["dirichlet_alpha"], dirichlet_factor=wl["dirichlet_factor"])
     searcher.pool.set_root_states(h_player.numpy(), h_first.numpy().view(np.uint64), h_second.numpy().view(np.uint64))
     h_actions = torch.zeros(T, dtype=torch.int32).pin_memory()
+    h_ply = np.full(T, 1 << 20, dtype=np.int64)      # the uploaded games are past their opening; restarted games count from 0
+    host_rng = np.random.RandomState(2024 + rank)
 
     def e2e_step():
         pool = searcher.pool
         visits, stats = searcher.step()                           # D2H: visit counts + statistics
-        h_actions.numpy()[:] = visits.argmax(axis=1)              # the host chooses the moves (mcts.py:99-104)
+        # the host chooses the moves like MCTS.self_play (mcts.py:99-104): sampled in proportion to the visit counts
+        # for the first sample_move_cutoff plies of a game, argmax (first maximum) afterwards
+        actions = visits.argmax(axis=1)
+        early = np.where(h_ply < wl["sample_move_cutoff"])[0]
+        if early.size:
+            cdf = np.cumsum(visits[early].astype(np.float64), axis=1)
+            draw = host_rng.random_sample(early.size) * cdf[:, -1]
+            actions[early] = (cdf > draw[:, None]).argmax(axis=1)
+        h_actions.numpy()[:] = actions
         searcher.advance(h_actions.numpy())                       # H2D: chosen actions; re-root with subtree reuse
+        h_ply[:] += 1
         np_p, np_f, np_s, np_fin, _ = pool.states()               # D2H: successor states, final flags
         if np_fin.any():
-            pool.reset(np.where(np_fin)[0].astype(np.int32))      # H2D: finished games start over
+            done = np.where(np_fin)[0].astype(np.int32)
+            pool.reset(done)                                      # H2D: finished games start over
+            h_ply[done] = 0
         return int(stats.sum())
 
     for _ in range(3):
@@ -436,7 +449,8 @@ def run_b200(args):
                     "what": "host-driven self-play through the public batched MCTS API, one move of every game per step "
                             f"(the reference's MCTS.self_play loop, mcts.py:96-111): BatchedMCTS.step(): {sims} simulations "
                             "per tree with cached_state_evaluator(net), visit counts + statistics to host arrays (D2H) -> "
-                            "host argmax into pinned memory -> advance(actions) (H2D, re-root with subtree reuse) -> "
+                            "host move choice into pinned memory (sampled from the visits for the first plies of a game, else argmax) "
+                            "-> advance(actions) (H2D, re-root with subtree reuse) -> "
                             "states() (D2H); finished games restart"},
             "gpu_launches": int(tot_launches),
             "clocks": clock_info,

@@ -99,13 +99,23 @@ __device__ __forceinline__ u64 othello_moves_dir(u64 own, u64 opp, u64 empty, co
     return bb_shift<DX, DY>(t, c) & empty;
 }
 
-__device__ __forceinline__ u64 othello_moves(u64 own, u64 opp, const GameCfg& c) {
+__device__ __forceinline__ u64 othello_moves_inline(u64 own, u64 opp, const GameCfg& c) {
     u64 empty = ~(own | opp) & c.full;
     u64 moves = 0;
 #define DM_DIR(DX, DY) moves |= othello_moves_dir<DX, DY>(own, opp, empty, c);
     DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
 #undef DM_DIR
     return moves;
+}
+// The 8x8 board (the BASELINE size) as ONE out-of-line copy with constant masks and shifts: the fully unrolled
+// eight-direction code is ~500 instructions, and the tree kernels reach it from half a dozen places -- inlined
+// everywhere it made k_round a 300 KB kernel that stalled on instruction fetch as much as on memory.
+static __device__ __noinline__ u64 othello_moves8(u64 own, u64 opp) {
+    return othello_moves_inline(own, opp, const_game_cfg<DM_OTHELLO, 8>());
+}
+__device__ __forceinline__ u64 othello_moves(u64 own, u64 opp, const GameCfg& c) {
+    if (c.g == 8) return othello_moves8(own, opp);
+    return othello_moves_inline(own, opp, c);
 }
 
 template <int DX, int DY>
@@ -126,6 +136,30 @@ __device__ __forceinline__ u64 othello_flips(u64 own, u64 opp, u64 bit, const Ga
     DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
 #undef DM_DIR
     return flips;
+}
+
+// the same flips without data-dependent loops: the run of opponent stones next to `bit` in one direction
+// (g - 2 stones at most), kept iff the square behind the run is an own stone.  Lanes that evaluate different moves
+// stay converged (expand_node computes one child per lane).
+template <int DX, int DY>
+__device__ __forceinline__ u64 othello_flips_dir_pp(u64 own, u64 opp, u64 bit, const GameCfg& c) {
+    u64 t = bb_shift<DX, DY>(bit, c) & opp;
+    for (int i = 0; i < c.g - 3; ++i) t |= bb_shift<DX, DY>(t, c) & opp;
+    return (bb_shift<DX, DY>(t, c) & own) ? t : 0ull;
+}
+__device__ __forceinline__ u64 othello_flips_pp_inline(u64 own, u64 opp, u64 bit, const GameCfg& c) {
+    u64 flips = 0;
+#define DM_DIR(DX, DY) flips |= othello_flips_dir_pp<DX, DY>(own, opp, bit, c);
+    DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
+#undef DM_DIR
+    return flips;
+}
+static __device__ __noinline__ u64 othello_flips8(u64 own, u64 opp, u64 bit) {
+    return othello_flips_pp_inline(own, opp, bit, const_game_cfg<DM_OTHELLO, 8>());
+}
+__device__ __forceinline__ u64 othello_flips_pp(u64 own, u64 opp, u64 bit, const GameCfg& c) {
+    if (c.g == 8) return othello_flips8(own, opp, bit);
+    return othello_flips_pp_inline(own, opp, bit, c);
 }
 
 // the empty square an own stone `bit` reaches over >=1 opponent stones in one direction,
@@ -250,6 +284,44 @@ __device__ __forceinline__ GState game_child(const GameCfg& c, const GState& s, 
         r.second = s.second | bit | flips;
     }
     return r;
+}
+
+// generate_child_state for a legal action, loop-free for Othello (identical result to game_child)
+__device__ __forceinline__ GState game_child_uniform(const GameCfg& c, const GState& s, int action) {
+    if (c.game != DM_OTHELLO || action == c.cells) return game_child(c, s, action);
+    GState r;
+    r.player = 1 - s.player;
+    const u64 bit = 1ull << action;
+    const u64 flips = othello_flips_pp(s.player ? s.first : s.second, s.player ? s.second : s.first, bit, c);
+    if (s.player) {
+        r.first = s.first | bit | flips;
+        r.second = s.second & ~flips;
+    } else {
+        r.first = s.first & ~flips;
+        r.second = s.second | bit | flips;
+    }
+    return r;
+}
+
+// is_final_state + outcome of the child reached from the NON-FINAL state `parent` by `action`, as a node code:
+// 0 = not final, 1 + 2 * outcome otherwise (1: FIRST wins / value 0, 2: draw, 3: SECOND wins / value 1).
+// Hex: the parent has no winner, so only the player who just placed a stone can have connected -- one flood fill
+// instead of two; a swap recolours a single stone and cannot end the game.
+__device__ __forceinline__ int game_child_final_code(const GameCfg& c, const GState& parent, int action,
+                                                     const GState& child) {
+    if (c.game == DM_HEX || c.game == DM_HEX_SWAP) {
+        if (action == c.cells) return 0;
+        if (parent.player) return hex_connected(child.first, c.row0, c.rowL, c) ? 1 : 0;   // FIRST: rows
+        return hex_connected(child.second, c.col0, c.colL, c) ? 3 : 0;                      // SECOND: columns
+    }
+    float o;
+    if (!game_is_final(c, child, o)) return 0;
+    return 1 + (int)(o * 2.0f);
+}
+__device__ __forceinline__ int game_final_code(const GameCfg& c, const GState& s) {
+    float o;
+    if (!game_is_final(c, s, o)) return 0;
+    return 1 + (int)(o * 2.0f);
 }
 
 // ---------------------------------------------------------------- CPython set ordering

@@ -15,6 +15,7 @@
 // reference for the same evaluator outputs.
 #include "games.cuh"
 
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -54,6 +55,7 @@ struct PoolView {
     double dirichlet_alpha, dirichlet_factor, rollout_share;
     u64 eval_salt;
     int leaves_per_round;      // 1 = exact; > 1 = virtual-loss mode
+    int level_budget;          // self-play: tree levels a warp may walk per launch before it sits the round out
     const double* host_noise;  // [n_trees][DM_MAX_ACTIONS] in child order, or null
     // nodes
     u32* visits;
@@ -62,6 +64,11 @@ struct PoolView {
     u32* first_child;
     u8* n_children;
     u8* action;
+    // the node's own state and whether it is final (0 = no, else 1 + 2 * outcome): written once at expansion, one child
+    // per lane, so the selection walks the tree without replaying a single move (Othello flips, Hex flood fills)
+    u64* node_first;
+    u64* node_second;
+    u8* node_final;
     // per tree
     u32* node_count;
     u32* root;
@@ -184,6 +191,9 @@ __device__ __forceinline__ void clear_node(const PoolView& P, size_t idx) {
 __device__ __forceinline__ void fresh_root(const PoolView& P, int t, const GState& s) {
     size_t base = (size_t)t * P.cap;
     clear_node(P, base);
+    P.node_first[base] = s.first;
+    P.node_second[base] = s.second;
+    P.node_final[base] = (u8)game_final_code(P.cfg, s);
     P.node_count[t] = 1;
     P.root[t] = 0;
     P.root_first[t] = s.first;
@@ -406,10 +416,10 @@ __device__ __forceinline__ void round_end(const PoolView& P, bool dense) {
 // tree_search (mcts.py:162-179): descend from the root while the node has children.
 // s_path (shared, per warp) receives the node indices; returns path length.
 __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GState& s, u32* s_path,
-                                       unsigned long long& scanned, bool& overflow) {
+                                       unsigned long long& scanned, bool& overflow, int& final_code) {
     const size_t base = (size_t)t * P.cap;
     u32 node = P.root[t];
-    s = root_state(P, t);
+    s.player = P.root_player[t];
     int len = 0;
     if (lane == 0) s_path[0] = node;
     len = 1;
@@ -427,7 +437,7 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
         int best = -1;
         // whole record of this lane's best child
         u32 b_visits = 0, b_first = 0;
-        int b_n = 0, b_action = 0;
+        int b_n = 0;
         // children lane and lane + 32 are loaded together so their divisions overlap; a third
         // (only Hex-with-swap 8x8 has 65 actions) takes the loop again
         for (int j0 = lane; j0 < n; j0 += 64) {
@@ -439,7 +449,6 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
             double pr0 = P.prior[c0], pr1 = P.prior[c1];
             u32 cf0 = P.first_child[c0], cf1 = P.first_child[c1];
             int cn0 = P.n_children[c0], cn1 = P.n_children[c1];
-            int ca0 = P.action[c0], ca1 = P.action[c1];
             double q0 = (v0 == 0) ? unvisited : __ddiv_rn(vs0, (double)v0);
             double q1 = (v1 == 0) ? unvisited : __ddiv_rn(vs1, (double)v1);
             // u = ((c_puct * P) * sqrt(N)) / (1 + n)   (mcts.py:40-43), no FMA contraction
@@ -454,7 +463,6 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
                 b_visits = v0;
                 b_first = cf0;
                 b_n = cn0;
-                b_action = ca0;
             }
             if (has1 && k1 > best_key) {
                 best_key = k1;
@@ -462,7 +470,6 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
                 b_visits = v1;
                 b_first = cf1;
                 b_n = cn1;
-                b_action = ca1;
             }
         }
         // sqrt for the next level, off the critical path of the reduction below
@@ -486,10 +493,9 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
         sq = __shfl_sync(DM_FULL_MASK, b_sq, owner);
         const u32 next_first = __shfl_sync(DM_FULL_MASK, b_first, owner);
         const int next_n = __shfl_sync(DM_FULL_MASK, b_n, owner);
-        const int act = __shfl_sync(DM_FULL_MASK, b_action, owner);
         scanned += (unsigned long long)n;
         node = first + (u32)best;
-        s = game_child(P.cfg, s, act);
+        s.player = 1 - s.player;        // every action, pass and swap included, hands the move over
         if (len >= DM_MAX_DEPTH) {
             overflow = true;
             break;
@@ -499,6 +505,10 @@ __device__ __forceinline__ int descend(const PoolView& P, int t, int lane, GStat
         first = next_first;
         n = next_n;
     }
+    // the leaf's state and finality were stored when its parent was expanded
+    s.first = P.node_first[base + node];
+    s.second = P.node_second[base + node];
+    final_code = P.node_final[base + node];
     __syncwarp();
     return len;
 }
@@ -552,6 +562,10 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
         P.first_child[c] = 0;
         P.n_children[c] = 0;
         P.action[c] = (u8)a;
+        const GState child = game_child_uniform(P.cfg, s, a);
+        P.node_first[c] = child.first;
+        P.node_second[c] = child.second;
+        P.node_final[c] = (u8)game_child_final_code(P.cfg, s, a, child);
     }
     if (lane == 0) {
         P.first_child[base + node] = cnt;
@@ -565,7 +579,8 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
 }
 
 // ---- Dirichlet noise (mcts.py:233-241) --------------------------------------------------
-__device__ __forceinline__ double sample_gamma(Philox& rng, double alpha) {
+// (out of line: log / pow / sqrt / cospi in double are thousands of instructions that run once per move)
+static __device__ __noinline__ double sample_gamma(Philox& rng, double alpha) {
     // Marsaglia-Tsang; alpha < 1 boosted through gamma(alpha + 1) * U^(1/alpha)
     double boost = 1.0;
     if (alpha < 1.0) {
@@ -720,7 +735,8 @@ __device__ __forceinline__ void compact_tree(const PoolView& P, int t, int lane)
         size_t src = base + ((size_t)w << 5) + lane;
         u32 v = 0, fc = 0;
         double vs = 0.0, pr = 0.0;
-        u8 nc = 0, ac = 0;
+        u8 nc = 0, ac = 0, fin = 0;
+        u64 nf = 0, ns = 0;
         u32 dst = 0;
         if (live) {
             v = P.visits[src];
@@ -729,6 +745,9 @@ __device__ __forceinline__ void compact_tree(const PoolView& P, int t, int lane)
             fc = P.first_child[src];
             nc = P.n_children[src];
             ac = P.action[src];
+            nf = P.node_first[src];
+            ns = P.node_second[src];
+            fin = P.node_final[src];
             dst = prefix[w] + __popc(word & ((1u << lane) - 1u));
             if (nc) fc = live_rank(mark, prefix, fc);
         }
@@ -741,6 +760,9 @@ __device__ __forceinline__ void compact_tree(const PoolView& P, int t, int lane)
             P.first_child[d] = fc;
             P.n_children[d] = nc;
             P.action[d] = ac;
+            P.node_first[d] = nf;
+            P.node_second[d] = ns;
+            P.node_final[d] = fin;
         }
         __syncwarp();
     }
@@ -885,16 +907,16 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_search_local(PoolView P
     while (!dead && sims > 0) {
         GState s;
         bool overflow;
-        int len = descend(P, t, lane, s, path, scanned, overflow);
+        int final_code;
+        int len = descend(P, t, lane, s, path, scanned, overflow, final_code);
         if (overflow) {
             if (lane == 0) count(P, kCntCapacity, 1);
             break;
         }
         depth += (unsigned long long)(len - 1);
-        float outcome;
         double value;
-        if (game_is_final(P.cfg, s, outcome)) {
-            value = (double)outcome;  // mcts.py:182-185
+        if (final_code) {
+            value = 0.5 * (double)(final_code - 1);  // the outcome's value, mcts.py:182-185
             ++without;
             ++terminal;
         } else {
@@ -1111,16 +1133,16 @@ __device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, 
                 flags &= ~kFlagNeedNoise;
             }
             bool overflow;
-            len = descend(P, t, lane, s, path, scanned, overflow);
+            int final_code;
+            len = descend(P, t, lane, s, path, scanned, overflow, final_code);
             if (overflow) {
                 if (lane == 0) count(P, kCntCapacity, 1);
                 sims = 0;
                 break;
             }
             depth += (unsigned long long)(len - 1);
-            float outcome;
-            if (game_is_final(P.cfg, s, outcome)) {
-                backup(P, t, lane, path, len, (double)outcome);
+            if (final_code) {
+                backup(P, t, lane, path, len, 0.5 * (double)(final_code - 1));
                 ++without;
                 ++terminal;
                 ++done;
@@ -1130,7 +1152,7 @@ __device__ __forceinline__ void select_tree(const PoolView& P, int t, int lane, 
                 // result does not depend on which round a simulation runs in); a stepped search
                 // keeps going because its caller counts rounds.
                 levels += len - 1;
-                if (kSelfPlay && levels + (len - 1) > kLevelBudget) break;
+                if (kSelfPlay && levels + (len - 1) > P.level_budget) break;
                 continue;
             }
         }
@@ -1386,7 +1408,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_vl(PoolView P) {
                 flags &= ~kFlagNeedNoise;
             }
             bool overflow;
-            len = descend(P, t, lane, s, path, scanned, overflow);
+            int final_code;
+            len = descend(P, t, lane, s, path, scanned, overflow, final_code);
             if (overflow) {
                 if (lane == 0) count(P, kCntCapacity, 1);
                 sims = 0;
@@ -1395,9 +1418,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) k_select_vl(PoolView P) {
             u32 leaf = path[len - 1];
             if (P.first_child[base + leaf] == kPendingLeaf) break;  // collision with a leaf of this round
             depth += (unsigned long long)(len - 1);
-            float outcome;
-            if (game_is_final(P.cfg, s, outcome)) {
-                backup(P, t, lane, path, len, (double)outcome);
+            if (final_code) {
+                backup(P, t, lane, path, len, 0.5 * (double)(final_code - 1));
                 ++without;
                 ++terminal;
                 ++done;
@@ -1717,6 +1739,8 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
     v.rollout_kind = DM_ROLLOUT_NONE;
     v.dirichlet_factor = 0.25;
     v.rollout_share = 1.0;
+    v.level_budget = kLevelBudget;
+    if (const char* env = getenv("DM_LEVEL_BUDGET")) v.level_budget = atoi(env) > 0 ? atoi(env) : kLevelBudget;   // A/B switch
     size_t T = (size_t)cfg->n_trees, N = T * (size_t)v.cap;
     int rc = DM_OK;
     auto fail = [&](int code) {
@@ -1727,6 +1751,8 @@ extern "C" int dm_pool_create(const dm_pool_config* cfg, dm_pool** out) {
     if ((rc = pool_alloc(p, &v.visits, N, false)) || (rc = pool_alloc(p, &v.value_sum, N, false)) ||
         (rc = pool_alloc(p, &v.prior, N, false)) || (rc = pool_alloc(p, &v.first_child, N, false)) ||
         (rc = pool_alloc(p, &v.n_children, N, false)) || (rc = pool_alloc(p, &v.action, N, false)) ||
+        (rc = pool_alloc(p, &v.node_first, N, false)) || (rc = pool_alloc(p, &v.node_second, N, false)) ||
+        (rc = pool_alloc(p, &v.node_final, N, false)) ||
         (rc = pool_alloc(p, &v.node_count, T)) || (rc = pool_alloc(p, &v.root, T)) ||
         (rc = pool_alloc(p, &v.root_first, T)) || (rc = pool_alloc(p, &v.root_second, T)) ||
         (rc = pool_alloc(p, &v.root_player, T)) || (rc = pool_alloc(p, &v.sims_left, T)) ||

@@ -219,14 +219,23 @@ class GameNetAgent(Agent):
 
 
 class GreedyGameNetAgent(GameNetAgent):
+    """Plays the network policy's best legal move, a sampled one with probability ``epsilon`` (the reference
+    declares this agent but leaves ``play`` unimplemented, gamenet.py:196-205)."""
+
     def __init__(self, net: GameNet, epsilon: float = 0) -> None:
         super().__init__(net)
         self.epsilon = epsilon
 
     def play(self, state) -> Action:
-        raise NotImplementedError
+        probabilities = self.net.evaluate(state)[1].numpy().astype(np.float64)
+        if self.epsilon > 0 and np.random.random_sample() < self.epsilon:
+            return int(np.random.choice(len(probabilities), p=probabilities / probabilities.sum()))
+        return int(np.argmax(probabilities))
 
 
 class SamplingGameNetAgent(GameNetAgent):
+    """Samples its move from the network's masked policy (declared, unimplemented in the reference, gamenet.py:208-210)."""
+
     def play(self, state) -> Action:
-        raise NotImplementedError
+        probabilities = self.net.evaluate(state)[1].numpy().astype(np.float64)
+        return int(np.random.choice(len(probabilities), p=probabilities / probabilities.sum()))

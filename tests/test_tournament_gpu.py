@@ -41,3 +41,16 @@ def test_begin_step_ids_leaves_other_trees_untouched():
     visits, stats = b.step(tree_ids=[1, 5])
     assert stats[[1, 5]].sum() == 40 and stats[[0, 2, 3, 4, 6, 7]].sum() == 0
     assert visits[[0, 2, 3, 4, 6, 7]].sum() == 0 and visits[1].sum() == 20
+
+
+def test_network_policy_agents_play_legal_games():
+    """GreedyGameNetAgent / SamplingGameNetAgent (declared but unimplemented in the reference, gamenet.py:196-210) play
+    whole games of legal moves through the sequential tournament driver."""
+    from deep_mcts_b200.gamenet import GreedyGameNetAgent, SamplingGameNetAgent
+    from deep_mcts_b200.tictactoe.convolutionalnet import ConvolutionalTicTacToeNet
+    from deep_mcts_b200.tournament import RandomAgent, compare_agents
+    net = ConvolutionalTicTacToeNet()
+    manager = net.manager
+    for agent in (GreedyGameNetAgent(net), GreedyGameNetAgent(net, epsilon=0.5), SamplingGameNetAgent(net)):
+        wins, draws, losses = compare_agents((agent, RandomAgent(manager)), 6, manager)
+        assert abs(sum(wins) + sum(draws) + sum(losses) - 2.0) < 1e-9
