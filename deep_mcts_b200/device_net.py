@@ -228,8 +228,16 @@ class DeviceNet:
         self.search_round(pool, fused=True)     # warm every kernel outside the capture (a real round: harmless,
         torch.cuda.synchronize(self.device)     # run_search's caller counts simulations, not rounds)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            self.search_round(pool, fused=True)
+        current = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(current)
+        with torch.cuda.stream(side):           # low-level capture: no gc / allocator flush per capture
+            graph.capture_begin(capture_error_mode="thread_local")
+            try:
+                self.search_round(pool, fused=True)
+            finally:
+                graph.capture_end()
+        current.wait_stream(side)
         self._graphs = {k: v for k, v in self._graphs.items() if v[2]() is not None}   # drop graphs of dead pools
         self._graphs[key] = (self.weights_version, graph, weakref.ref(pool))
         return graph

@@ -70,6 +70,7 @@ class BatchedSelfPlay:
         self.tree_timers = None     # set to a list to collect CUDA-event pairs around the tree kernels
         self.use_graph = False      # set True to replay one captured round instead of re-launching it
         self._graph = None
+        self._warmed = False        # every kernel of the round has run once (needed only before the first capture)
         self._phase_offset = False  # pools[1:] hold a pending selection (pipelined graph mode)
         self._graph_launches = 0
         self.graph_replays = 0
@@ -147,33 +148,52 @@ class BatchedSelfPlay:
         for st in self.streams:
             current.wait_stream(st)
 
+    @staticmethod
+    def _capture(fn) -> "torch.cuda.CUDAGraph":
+        """Capture ``fn`` on a side stream with the low-level API: no device synchronisation, no gc / cache flush
+        (``torch.cuda.graph`` does all three), so re-capturing after a weight transfer costs a fraction of a
+        millisecond and does not stall the training stream."""
+        graph = torch.cuda.CUDAGraph()
+        current = torch.cuda.current_stream()
+        side = torch.cuda.Stream(device=current.device)
+        side.wait_stream(current)
+        with torch.cuda.stream(side):
+            graph.capture_begin(capture_error_mode="thread_local")
+            try:
+                fn()
+            finally:
+                graph.capture_end()
+        current.wait_stream(side)
+        return graph
+
     def _capture_round(self) -> None:
         """Capture one fused round (tree kernel: expand/backup of the previous batch and the next selection into
         dense leaf slots, then the network kernels) into a CUDA graph; the round has no host-visible state, so
         replaying it is identical to launching it."""
         dn, pool = self.device_nets[0], self.pools[0]
-        dn.search_round(pool, selfplay=True, fused=True)        # warm every kernel outside the capture
-        torch.cuda.synchronize()
+        if not self._warmed:
+            dn.search_round(pool, selfplay=True, fused=True)    # first capture: load every kernel outside the capture
+            torch.cuda.synchronize()
+            self._warmed = True
         lib = _lib.load()
         before = lib.dm_launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
-            dn.search_round(pool, selfplay=True, fused=True)
+        self._graph = self._capture(lambda: dn.search_round(pool, selfplay=True, fused=True))
         self._graph_launches = int(lib.dm_launch_count() - before)
-        self._graph = graph
 
     def _capture_pipelined_round(self) -> None:
         """One graph with a branch per pool.  Pool 0's branch is select -> network -> expand/backup;
         the other pools run a phase apart, network -> expand/backup -> select (their selection for
         the next replay), so a pool's tree kernels are in flight while another pool's trunk
         occupies the tensor cores.  Every pool still does exactly one round per replay."""
-        for dn, pool in zip(self.device_nets, self.pools):
-            dn.search_round(pool, selfplay=True)    # warm every kernel outside the capture
-        torch.cuda.synchronize()
+        if not self._warmed:
+            for dn, pool in zip(self.device_nets, self.pools):
+                dn.search_round(pool, selfplay=True)    # first capture: load every kernel outside the capture
+            torch.cuda.synchronize()
+            self._warmed = True
         lib = _lib.load()
         before = lib.dm_launch_count()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+
+        def body():
             current = torch.cuda.current_stream()
             for st in self.streams:
                 st.wait_stream(current)
@@ -186,8 +206,9 @@ class BatchedSelfPlay:
                         pool.selfplay_select()
             for st in self.streams:
                 current.wait_stream(st)
+
+        self._graph = self._capture(body)
         self._graph_launches = int(lib.dm_launch_count() - before)
-        self._graph = graph
 
     def graph_launches(self) -> int:
         """Kernel launches executed through graph replays so far."""
@@ -207,8 +228,24 @@ class BatchedSelfPlay:
     def positions_written(self) -> int:
         return sum(pool.positions_written() for pool in self.pools)
 
+    def replay_snapshot(self, max_games: Optional[int] = None, protect: int = 0):
+        """[(pool, lo, hi)]: per pool the range of (monotonic) replay positions a trainer may read -- complete now,
+        inside the window of the last ``max_games`` games, and not among the ``protect`` ring slots that come next in
+        line to be overwritten.  ``protect`` = the most positions self-play can append while the snapshot is in use
+        (n_trees x DM_MAX_DEPTH per block covers every case: a tree finishes at most one game per block) makes reads
+        through the snapshot race-free while ``run_rounds`` is in flight on another stream.  Synchronises once."""
+        ranges = []
+        for pool, size in zip(self.pools, self.pool_sizes):
+            hi, _ = pool.replay_progress()
+            lo = max(0, hi - pool.replay_capacity + min(int(protect), pool.replay_capacity))
+            if max_games is not None:
+                lo = max(lo, pool.replay_window_start(max(1, int(max_games) * size // self.n_trees)))
+            if hi > lo:
+                ranges.append((pool, lo, hi))
+        return ranges
+
     def sample_batch(self, batch_size: int, generator: Optional[torch.Generator] = None,
-                     max_games: Optional[int] = None
+                     max_games: Optional[int] = None, snapshot=None
                      ) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor, torch.Tensor]:
         """Uniform sample over the replay rings: (first, second, player, pi[B, A], z[B, 1]) on the device.
         The reference picks a game with probability proportional to its length, then one of its positions
@@ -216,18 +253,13 @@ class BatchedSelfPlay:
         the last ``max_games`` finished games (the reference trims its buffer to ``replay_buffer_max_size``
         GAMES, train.py:149-151); with several pools every pool contributes its share of that window.
 
-        The sample reads the rings on the current stream: take it while self-play is idle (or ordered before
-        it on the same stream), never concurrently with ``run_rounds`` on another stream."""
+        The sample reads the rings on the current stream: take it while self-play is idle (or ordered before it on
+        the same stream), or pass a ``snapshot`` from ``replay_snapshot(max_games, protect)`` taken before self-play
+        was launched -- then no host synchronisation happens here and the reads stay clear of the slots being
+        written."""
         dev = self.pool.device
         A = self.pool.num_actions
-        ranges = []
-        for pool, size in zip(self.pools, self.pool_sizes):
-            hi, _ = pool.replay_progress()
-            lo = max(0, hi - pool.replay_capacity)
-            if max_games is not None:
-                lo = max(lo, pool.replay_window_start(max(1, int(max_games) * size // self.n_trees)))
-            if hi > lo:
-                ranges.append((pool, lo, hi))
+        ranges = snapshot if snapshot is not None else self.replay_snapshot(max_games)
         total = sum(hi - lo for _, lo, hi in ranges)
         if total == 0:
             raise RuntimeError("replay ring is empty")

@@ -67,6 +67,9 @@ class TrainingConfiguration:
     uniform_until_first_transfer: bool = True
     precision: Optional[str] = None
     overlap_training: bool = True    # SGD steps run on their own stream while the next self-play block is searched
+    # replay the SGD step (forward, backward, all-reduce, update) as one CUDA graph.  Off by default: measured +2 % at
+    # 8 GPUs (batch 128 per GPU), nothing at 1 GPU -- the step is cuDNN time, not launch latency
+    graph_train_step: bool = False
 
     def to_json_dict(self) -> Dict[str, Any]:
         d = asdict(self)
@@ -121,6 +124,9 @@ class SelfPlayTrainer:
         self.generator.manual_seed(1234 + self.rank)
         self.engine.use_graph = True
         self.sp_stream = torch.cuda.Stream(device=self.device) if config.overlap_training else None
+        self._train_graph = None         # CUDA graph of one whole SGD step (see _sgd)
+        self._train_stream = None
+        self._eager_steps = 0
 
     # ---- self-play -------------------------------------------------------------------
     def _uniform_round(self) -> None:
@@ -152,37 +158,83 @@ class SelfPlayTrainer:
 
     def block(self, train_steps: int):
         """One block of the loop: ``num_simulations`` search rounds for every game and ``train_steps`` SGD steps.
-        With ``overlap_training`` the two run concurrently on two streams.  The steps' batches are gathered from
-        the replay ring BEFORE the block's self-play is launched, so the SGD stream never reads a ring slot the
-        search is overwriting; the weight transfer happens at the block boundary, when both streams are idle.
+        With ``overlap_training`` the two run concurrently on two streams.  The steps sample through a snapshot of
+        the replay ring taken BEFORE the block's self-play is launched -- positions complete at that moment, minus the
+        ring slots the block can overwrite (at most one finished game = DM_MAX_DEPTH positions per tree) -- so the SGD
+        stream never reads a slot the search is writing and never synchronises with it; the weight transfer happens at
+        the block boundary, when both streams are idle.
         Returns the list of (policy_loss, value_loss, accuracy) of the steps taken."""
         if self.sp_stream is None or self.uniform_phase:
             self.self_play_block()
             return [self.train_step() for _ in range(train_steps)] if self.have_examples() else []
         main = torch.cuda.current_stream()
-        batches = [self.sample() for _ in range(train_steps)] if self.have_examples() else []
+        have = self.have_examples()
+        snapshot = self.snapshot() if have else None
+        # a ring too small to keep a protected range (tiny test configurations): gather the batches before self-play starts
+        batches = [self.sample() for _ in range(train_steps)] if have and not snapshot else None
         self.sp_stream.wait_stream(main)
         with torch.cuda.stream(self.sp_stream):
             self.self_play_block()
-        losses = [self.train_step(batch, defer_transfer=True) for batch in batches]
+        losses = []
+        for i in range(train_steps if have else 0):
+            batch = batches[i] if batches is not None else \
+                self.engine.sample_batch(self.config.batch_size, self.generator, snapshot=snapshot)
+            losses.append(self.train_step(batch, defer_transfer=True))
         main.wait_stream(self.sp_stream)
         if self._transfer_due:
             self._transfer_weights()
         return losses
 
     # ---- training --------------------------------------------------------------------
+    def snapshot(self):
+        """Replay ranges the block's SGD steps may read while its self-play runs (see ``block``)."""
+        return self.engine.replay_snapshot(max(1, self.config.replay_buffer_max_size // self.world),
+                                           protect=self.config.n_trees * _lib.DM_MAX_DEPTH)
+
     def sample(self):
         """One training batch from the last ``replay_buffer_max_size`` games (train.py:149-151, 337-348);
         every rank holds its share of that window."""
         return self.engine.sample_batch(self.config.batch_size, self.generator,
                                         max_games=max(1, self.config.replay_buffer_max_size // self.world))
 
+    def _sgd(self, planes: torch.Tensor, pi: torch.Tensor, z: torch.Tensor):
+        """``GameNet.train`` on one batch.  The step is ~150 small kernels (batch 1024 / world on a 1.6 M-parameter
+        net) and launch-bound when issued eagerly, so after a few eager steps (optimizer state allocated, cuDNN
+        autotuned) the whole step -- forward, backward, the in-place gradient all-reduce, the SGD update -- is
+        captured once into a CUDA graph over static input buffers and replayed from then on."""
+        if not self.config.graph_train_step or not planes.is_cuda:
+            return self.net.train(planes, pi, z)
+        if self._train_graph is None:
+            current = torch.cuda.current_stream()
+            if self._train_stream is None:
+                self._train_stream = torch.cuda.Stream(device=self.device)
+            if self._eager_steps < 3 or planes.shape[0] != self.config.batch_size:
+                # warm-up steps run on the stream the capture will use: autograd's gradient accumulators belong to
+                # the stream of the first forward pass, and a capture that has to synchronise with another stream
+                # for them is invalidated
+                self._eager_steps += 1
+                self._train_stream.wait_stream(current)
+                with torch.cuda.stream(self._train_stream):
+                    losses = self.net.train(planes, pi, z)
+                current.wait_stream(self._train_stream)
+                return losses
+            self._static = (planes.clone(), pi.clone(), z.clone())
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=self._train_stream):
+                self._static_losses = self.net.train(*self._static)
+            self._train_graph = graph
+        for dst, src in zip(self._static, (planes, pi, z)):
+            dst.copy_(src)
+        self._train_graph.replay()
+        self.net._device_net_stale = True
+        return tuple(t.clone() for t in self._static_losses)
+
     def train_step(self, batch=None, defer_transfer: bool = False):
         first, second, player, pi, z = batch if batch is not None else self.sample()
         planes = bitboards_to_planes(first, second, player, self.net.manager.board, self.transpose)
         if pi.shape[1:] != tuple(self.net.net.policy_head.out_shape):
             pi = pi.reshape(pi.shape[0], *self.net.net.policy_head.out_shape)
-        losses = self.net.train(planes, pi, z)
+        losses = self._sgd(planes, pi, z)
         self.iterations += 1
         if self.iterations % self.config.transfer_interval == 0:
             if defer_transfer:

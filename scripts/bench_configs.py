@@ -89,7 +89,7 @@ def rollouts(rank, world):
         del m
 
 
-def train(rank, world):
+def train(rank, world, overlap=True, graph_step=True):
     from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
     from deep_mcts_b200.train import SelfPlayTrainer, TrainingConfiguration
     torch.manual_seed(0)
@@ -97,7 +97,7 @@ def train(rank, world):
     cfg = TrainingConfiguration(num_games=1000, num_simulations=50, save_interval=0, evaluation_interval=0,
                                 save_dir="/tmp", sample_move_cutoff=10, dirichlet_alpha=1.0, replay_buffer_max_size=5000,
                                 batch_size=1024 // world, n_trees=4096, train_steps_per_block=8, transfer_interval=16,
-                                uniform_until_first_transfer=False)
+                                uniform_until_first_transfer=False, overlap_training=overlap, graph_train_step=graph_step)
     tr = SelfPlayTrainer(net, cfg)
     for _ in range(70):           # fill the replay ring with finished games first
         tr.self_play_block()
@@ -141,7 +141,7 @@ def train(rank, world):
                           "train_steps_per_sec": sums["steps"] / world / maxima["s"],
                           "gradient_allreduce_us": allreduce_us, "gradient_elements": n_elems,
                           "train_steps_per_block": cfg.train_steps_per_block,
-                          "overlap_training": cfg.overlap_training}))
+                          "overlap_training": cfg.overlap_training, "graph_train_step": cfg.graph_train_step}))
 
 
 def engines(rank, world):
@@ -204,6 +204,10 @@ def engines(rank, world):
 if __name__ == "__main__":
     rank, world = setup()
     which = sys.argv[1] if len(sys.argv) > 1 else "rollouts"
-    {"rollouts": rollouts, "train": train, "engines": engines}[which](rank, world)
+    if which.startswith("train"):
+        # train | train-serial | train-eager | train-serial-eager
+        train(rank, world, overlap="serial" not in which, graph_step="eager" not in which)
+    else:
+        {"rollouts": rollouts, "engines": engines}[which](rank, world)
     if world > 1:
         dist.destroy_process_group()

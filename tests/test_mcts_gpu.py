@@ -473,3 +473,63 @@ def test_full_games_match_reference_mcts_digests(golden_dir, entry_index):
     wrong = [k for k in range(T) if got[k] != entry["digests"][k]]
     assert not wrong, f"{len(wrong)} of {T} games differ from the reference, first: game {wrong[0]}"
     assert batch.pool.counters()["capacity_errors"] == 0
+
+
+def test_python_rollout_policy_next_to_a_network_evaluator_is_played():
+    """evaluate_leaf with BOTH a state evaluator and a rollout policy returns (rollout + value) / 2 (mcts.py:187-196).
+    A Python rollout policy next to a GameNet evaluator must go through the leaf exchange (network batch on the
+    device, playout on the host) -- not silently drop the rollouts.  Deterministic policy => same visits as the oracle."""
+    import numpy as np
+    from deep_mcts_b200.gamenet import cached_state_evaluator
+    from deep_mcts_b200.mcts import MCTS
+    from deep_mcts_b200.othello.convolutionalnet import ConvolutionalOthelloNet
+    from oracle import net as onet
+    from oracle.synth import synthetic_state_dict
+    game = make_game("othello", 6)
+    sd = synthetic_state_dict(game, 32, 1, 32, seed=5, conv_gain=1.0, fc_scale=1.0)
+    net = ConvolutionalOthelloNet(6, num_residual=1, channels=32, value_head_hidden_units=32)
+    net.load_state_dict(sd)
+    net.precision = "fp32"
+    manager = net.manager
+    first_legal = lambda state: min(manager.legal_actions(state))       # noqa: E731  (a plain Python callable)
+    m = MCTS(manager, 20, first_legal, cached_state_evaluator(net))
+    oracle_eval = onet.make_evaluator(sd)
+    ref = OracleMCTS(game, 20, lambda g, s: min(g.legal_list(s)), oracle_eval)
+    for _ in range(2):
+        dist, stats = m.step()
+        ref_dist, ref_stats = ref.step()
+        assert tuple(stats) == tuple(ref_stats)
+        visits, _ = m.pool.root_visits()
+        assert [int(v) for v in visits[0][: game.num_actions]] == ref.root_visit_counts()
+        a = int(np.argmax(dist))
+        m.advance(a)
+        ref.advance(a)
+    assert m.pool.counters()["rollout_plies"] == 0        # the playouts ran on the host, not in the device kernels
+
+
+def test_virtual_loss_mode_rejects_rollout_policies():
+    from deep_mcts_b200 import mcts as dm
+    manager = manager_for("othello", 6)
+    b = dm.BatchedMCTS(manager, 4, 16, dm.random_rollout_policy(manager), lambda s: (0.5, [1 / 37] * 37), leaves_per_round=4)
+    with pytest.raises(ValueError):
+        b.step()
+
+
+def test_capacity_error_is_reported_once_and_the_pool_stays_usable():
+    """A tree that outgrows its arena raises once (DM_ERR_CAPACITY); later counter reads succeed again, and a
+    self-play tree whose root could not be expanded restarts instead of re-rooting on garbage."""
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200._lib import DeepMctsError
+    from deep_mcts_b200.pool import TreePool
+    manager = manager_for("othello", 8)
+    pool = TreePool(manager, 8, 24, compaction=False)          # 24 node slots: a few expansions at most
+    pool.configure(30, _lib.DM_EVAL_UNIFORM, _lib.DM_ROLLOUT_NONE, 0, 0.0, 0.25)
+    pool.begin_step()
+    pool.search_local()
+    with pytest.raises(DeepMctsError):
+        pool.counters()
+    c = pool.counters()                                         # not sticky
+    assert c["capacity_errors"] > 0
+    pool.reset()
+    pool.begin_step()
+    assert pool.counters()["capacity_errors"] == c["capacity_errors"]
