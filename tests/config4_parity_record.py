@@ -3,7 +3,7 @@
 without the state evaluator, on the device (batched tournament) next to the committed oracle games
 (tests/golden/config4_<case>.json).  Prints one JSON line per pairing with both win rates and their 95 % intervals.
 
-    python scripts/config4_parity.py [case ...] > profiles/config4_parity_r2.jsonl
+    python tests/config4_parity_record.py [case ...] > profiles/config4_parity_r2.jsonl
 """
 import json
 import sys

@@ -61,7 +61,9 @@ def test_complex_vs_simple_rollout_agents_match_the_oracle(golden_dir, case, wit
     want = data["pairings"][name]
     cfg = data["config"]
     games = 480 if case == "small7" else 240
-    got = run_device_pairing(cfg, with_evaluator, games, seed=3)
+    # small7 runs the fp32 kernels (same arithmetic as the oracle's network); full6 runs the bf16 tensor-core path
+    # (the fp32 CUDA-core path needs two minutes per pairing at C=128; tests/config4_parity_record.py records both)
+    got = run_device_pairing(cfg, with_evaluator, games, seed=3, precision="fp32" if case == "small7" else "bf16")
     for side in ("first", "second"):
         ok, p_dev, p_cpu, sigma = within_binomial_bounds(got[f"complex_wins_as_{side}"], got[f"games_as_{side}"],
                                                          want[f"complex_wins_as_{side}"], want[f"games_as_{side}"], 4.0)
