@@ -83,12 +83,18 @@ def ncu_dram_traffic_per_launch():
 def tree_roofline(pd, tree_ms, peaks):
     """HBM roofline of the tree kernel(s) from the run's own counters (SURVEY 8(d) byte model with
     f64 priors: child record visits 4 + value_sum 8 + prior 8 = 20 B, node header 16 B, path entry 4 B,
-    state 17 B; expansion writes 26 B per child and reads 4*65 + 4 B of evaluator output; backup is a
-    12 B read + 12 B write per path node).  A single pool runs both phases in one kernel (k_round)."""
+    state 17 B; expansion writes 26 B of node record + 17 B of stored state per child and reads 4*65 + 4 B of
+    evaluator output; backup is a 12 B read + 12 B write per path node; plus the evaluation cache's probes, row
+    copies and inserts).  A single pool runs both phases in one kernel (k_round)."""
     sims, depth, scanned = pd["simulations"], pd["depth_sum"], pd["children_scanned"]
     created, evals = pd["children_created"], pd["leaf_evals"]
-    select_bytes = 16 * depth + 20 * scanned + 17 * sims + 4 * (depth + sims)
-    expand_bytes = evals * (16 + 4 * 65 + 4) + 26 * created + 24 * (depth + sims)
+    hits, inserts = pd.get("cache_hits", 0), pd.get("cache_inserts", 0)
+    # selection: child records + headers along the path, the root state, the leaf's stored state and finality (17 B),
+    # the path; evaluation-cache probe of every non-terminal leaf: 8 ways x (ctl 8 B + key 16 B)
+    select_bytes = 16 * depth + 20 * scanned + 17 * sims + 17 * sims + 4 * (depth + sims) + (evals + hits) * 8 * 24
+    # expansion: evaluator row in, 26 B node record + 17 B stored state per child out, backup RMW along the path;
+    # cache: a hit copies a 272 B row out and back in, an insert writes a 272 B row + 24 B header
+    expand_bytes = (evals + hits) * (16 + 4 * 65 + 4) + 43 * created + 24 * (depth + sims) + hits * 272 + inserts * 296
     peak = float(peaks.get("hbm_gbs", 6650.0)) if peaks else 6650.0
     out = {"bound": "hbm", "peak": peak, "unit": "GB/s",
            "note": "pointer-chasing kernels: dependent-load latency bound, far below the bandwidth roofline by construction"}

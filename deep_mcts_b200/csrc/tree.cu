@@ -1056,17 +1056,38 @@ __device__ __forceinline__ void finish_move(const PoolView& P, int t, int lane) 
         const unsigned long long slot0 = packed & ((1ull << DM_REPLAY_POS_BITS) - 1ull);
         if (lane == 0) P.rp_game_end[(packed >> DM_REPLAY_POS_BITS) & (DM_REPLAY_GAME_RING - 1)] = slot0 + cnt;
         float z = outcome * 2.0f - 1.0f;  // train.py:270-272
-        for (u32 i = 0; i < cnt; ++i) {
-            size_t e = (size_t)t * DM_MAX_DEPTH + i;
-            size_t r = (size_t)((slot0 + i) % P.replay_cap);
-            for (int j = lane; j < DM_MAX_ACTIONS; j += 32)
-                P.rp_pi[r * DM_MAX_ACTIONS + j] = P.ex_pi[e * DM_MAX_ACTIONS + j];
-            if (lane == 0) {
-                u8 pl = P.ex_player[e];
-                P.rp_first[r] = P.ex_first[e];
-                P.rp_second[r] = P.ex_second[e];
-                P.rp_player[r] = pl;
-                P.rp_z[r] = (pl == 0) ? z : -z;  // train.py:278-280
+        // The game's positions are one contiguous block in the per-tree record and (up to the ring's wrap-around)
+        // in the replay ring.  This runs in the one or two warps per launch whose game just ended and sets the
+        // launch's critical path, so it is written for memory-level parallelism: states / player / z one position
+        // per lane, the visit distributions as a flat copy with eight loads in flight per lane.
+        const size_t e0 = (size_t)t * DM_MAX_DEPTH;
+        for (u32 i = lane; i < cnt; i += 32) {
+            const size_t r = (size_t)((slot0 + i) % P.replay_cap);
+            const u8 pl = P.ex_player[e0 + i];
+            P.rp_first[r] = P.ex_first[e0 + i];
+            P.rp_second[r] = P.ex_second[e0 + i];
+            P.rp_player[r] = pl;
+            P.rp_z[r] = (pl == 0) ? z : -z;  // train.py:278-280
+        }
+        const float* src = P.ex_pi + e0 * DM_MAX_ACTIONS;
+        const u32 total_f = cnt * DM_MAX_ACTIONS;
+        const size_t ring_f = (size_t)P.replay_cap * DM_MAX_ACTIONS;
+        const size_t dst0 = (size_t)(slot0 % P.replay_cap) * DM_MAX_ACTIONS;
+        for (u32 k0 = 0; k0 < total_f; k0 += 8 * 32) {
+            float v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const u32 k = k0 + (u32)u * 32 + (u32)lane;
+                v[u] = k < total_f ? src[k] : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const u32 k = k0 + (u32)u * 32 + (u32)lane;
+                if (k < total_f) {
+                    size_t d = dst0 + k;
+                    while (d >= ring_f) d -= ring_f;    // the block wraps around the end of the ring (once, unless the ring is tiny)
+                    P.rp_pi[d] = v[u];
+                }
             }
         }
         if (lane == 0) {
