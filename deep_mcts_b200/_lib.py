@@ -81,6 +81,7 @@ _SIGNATURES = {
     "dm_pool_leaf_buffers": (c_int, [_P, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                      POINTER(c_void_p), POINTER(c_void_p)]),
     "dm_pool_leaf_index": (c_int, [_P, POINTER(c_void_p)]),
+    "dm_pool_debug_timing": (c_int, [_P, POINTER(c_void_p)]),
     "dm_pool_cache_enable": (c_int, [_P, c_int, c_int]),
     "dm_pool_cache_clear": (c_int, [_P, _P]),
     "dm_pool_expand_backup": (c_int, [_P, _P, c_int, _P, c_int, _P]),

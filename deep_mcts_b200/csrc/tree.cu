@@ -121,6 +121,7 @@ struct PoolView {
     u32* cround;                // [0] search-round stamp, [1] blocks finished in the running launch
     int* pend_centry;           // [n_trees] entry claimed for the pending leaf (-1: none)
     unsigned long long* pend_cctl;  // [n_trees] the pending ctl word that claim published
+    unsigned long long* dbg_warp;   // [n_trees][4] optional per-warp timing of k_round (dm_pool_debug_timing), else null
     u8* leaf_live;              // [n_trees] dense mode: 1 = slot t holds a leaf the evaluator must run
     int* leaf_index;            // [n_trees] dense mode: compacted list of the live slots (count in leaf_count)
     // self-play recording
@@ -579,23 +580,30 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
 }
 
 // ---- Dirichlet noise (mcts.py:233-241) --------------------------------------------------
-// (out of line: log / pow / sqrt / cospi in double are thousands of instructions that run once per move)
-static __device__ __noinline__ double sample_gamma(Philox& rng, double alpha) {
-    // Marsaglia-Tsang; alpha < 1 boosted through gamma(alpha + 1) * U^(1/alpha)
-    double boost = 1.0;
-    if (alpha < 1.0) {
-        boost = pow(rng.uniform(), 1.0 / alpha);
-        alpha += 1.0;
+// Gamma(alpha, 1) by Marsaglia-Tsang; alpha < 1 boosted through gamma(alpha + 1) * U^(1/alpha).  Single precision
+// on purpose: the sample is only ever used as a random number (it is normalised and mixed into the priors in
+// double), and the double-precision log / pow / cospi sequences made the ~2 % of trees that start a new move in a
+// launch run 5-7x longer than all the others -- on Hex 7x7 (49 children, alpha 0.33: two boosted samples per lane)
+// that single tail set the duration of the whole tree kernel (profiles/tree_tail_probe_r2.jsonl).
+__device__ __forceinline__ float uniform_open_f(Philox& rng) {
+    return ((float)(rng.next() >> 8) + 0.5f) * (1.0f / 16777216.0f);   // (0, 1), 24 bits
+}
+__device__ __forceinline__ double sample_gamma(Philox& rng, double alpha_d) {
+    float alpha = (float)alpha_d;
+    float boost = 1.0f;
+    if (alpha < 1.0f) {
+        boost = powf(uniform_open_f(rng), 1.0f / alpha);
+        alpha += 1.0f;
     }
-    double d = alpha - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    const float d = alpha - 1.0f / 3.0f, c = rsqrtf(9.0f * d);
     while (true) {
-        double u1 = rng.uniform(), u2 = rng.uniform();
-        double x = sqrt(-2.0 * log(u1)) * cospi(2.0 * u2);
-        double v = 1.0 + c * x;
-        if (v <= 0.0) continue;
+        const float u1 = uniform_open_f(rng), u2 = uniform_open_f(rng);
+        const float x = sqrtf(-2.0f * logf(u1)) * cospif(2.0f * u2);
+        float v = 1.0f + c * x;
+        if (v <= 0.0f) continue;
         v = v * v * v;
-        double u = rng.uniform();
-        if (log(u) < 0.5 * x * x + d - d * v + d * log(v)) return d * v * boost;
+        const float u = uniform_open_f(rng);
+        if (logf(u) < 0.5f * x * x + d - d * v + d * logf(v)) return (double)(d * v * boost);
     }
 }
 
@@ -618,7 +626,11 @@ __device__ __forceinline__ void apply_root_noise(const PoolView& P, int t, int l
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(DM_FULL_MASK, sum, off);
-        for (int k = 0; k < 3; ++k) noise[k] /= sum;
+        if (sum > 0.0) {
+            for (int k = 0; k < 3; ++k) noise[k] /= sum;
+        } else {   // every sample underflowed (alpha far below the reference's 0.33): fall back to no preference
+            for (int k = 0; k < 3; ++k) noise[k] = 1.0 / (double)n;
+        }
         __syncwarp();
         if (lane == 0) P.rng_ctr[t] += 64;
     }
@@ -666,7 +678,7 @@ __device__ __forceinline__ double mix_rollout(const PoolView& P, const GState& s
 
 // ---- arena compaction ---------------------------------------------------------------------
 // Re-rooting with subtree reuse (mcts.py:105-108) leaves the rest of the old tree unreachable.
-// When a tree's arena is more than half full at a re-root, the live subtree is slid to the front
+// When a tree's arena cannot be sure to hold the next move's search at a re-root, the live subtree is slid to the front
 // in place: (1) mark live nodes in one forward pass (children are always allocated after their
 // parent, so marks flow forward), (2) prefix-count the marks per 32-node word, (3) move every
 // live node to its rank.  Order is preserved, so contiguous child blocks stay contiguous, ranks
@@ -679,7 +691,12 @@ __device__ __forceinline__ u32 live_rank(const u32* mark, const u32* prefix, u32
 __device__ __forceinline__ void compact_tree(const PoolView& P, int t, int lane) {
     if (!P.cmark) return;
     const u32 used = P.node_count[t];
-    if (used <= P.cap / 2) return;
+    // compact only when the next move might not fit: a move expands at most (simulations + root) leaves of at most
+    // num_actions children each.  (A pass over a 36 k-node Hex arena is ~0.2 ms for that one warp -- longer than the
+    // whole launch otherwise takes -- so it must not run "when half full" but when it is needed.)
+    const unsigned long long move_worst = (unsigned long long)(P.num_simulations + 2) * (unsigned long long)P.cfg.num_actions;
+    const u32 need = (u32)min(move_worst, (unsigned long long)(P.cap / 2));
+    if (used + need <= P.cap) return;
     const size_t base = (size_t)t * P.cap;
     u32* mark = P.cmark + (size_t)t * P.cap_words;
     u32* prefix = P.cprefix + (size_t)t * P.cap_words;
@@ -1353,6 +1370,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
     P.scnt = s_cnt[warp];
     const u32 now = __ldcv(P.cround);
     if (t < P.n_trees) {
+        const long long t0 = P.dbg_warp ? clock64() : 0;
         counters_begin(P.scnt, lane);
         if (P.path_len[t] > 0) {
             GState s;
@@ -1361,7 +1379,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
             s.player = P.pend_player[t];
             expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
         }
+        const long long t1 = P.dbg_warp ? clock64() : 0;
         select_tree<kSelfPlay, kSelfPlay>(P, t, lane, s_path[warp], now);
+        if (P.dbg_warp && lane == 0) {   // diagnostics: cycles of the two phases, what the selection did this round
+            const long long t2 = clock64();
+            unsigned long long* d = P.dbg_warp + (size_t)t * 4;
+            d[0] = (unsigned long long)(t1 - t0);
+            d[1] = (unsigned long long)(t2 - t1);
+            d[2] = ((unsigned long long)P.scnt[kCntMoves] << 32) | ((unsigned long long)P.scnt[kCntGames] << 24) |
+                   ((unsigned long long)P.scnt[kCntTerminal] << 16) | (unsigned long long)P.scnt[kCntDepth];
+            d[3] = (unsigned long long)P.scnt[kCntScanned];
+        }
         counters_flush(P, t, P.scnt, lane);
     }
     round_end(P, kSelfPlay);   // dense leaf batch (self-play): the last block compacts the live slots
@@ -1985,6 +2013,17 @@ extern "C" int dm_pool_cache_clear(dm_pool* p, void* stream) {
     if (!p->v.cctl) return DM_OK;
     // entries that are pending right now are dropped as well: their owners find another ctl word and skip the store
     DM_CUDA(cudaMemsetAsync(p->v.cctl, 0, ((size_t)p->v.cmask + 1) * sizeof(unsigned long long), (cudaStream_t)stream));
+    return DM_OK;
+}
+
+extern "C" int dm_pool_debug_timing(dm_pool* p, uint64_t** per_tree) {
+    DM_CHECK_ARG(p && per_tree, "dm_pool_debug_timing: null argument");
+    if (!p->v.dbg_warp) {
+        DM_CUDA(cudaSetDevice(p->cfg.device));
+        DM_CUDA(cudaDeviceSynchronize());
+        DM_TRY(pool_alloc(p, &p->v.dbg_warp, (size_t)p->v.n_trees * 4));
+    }
+    *per_tree = (uint64_t*)p->v.dbg_warp;
     return DM_OK;
 }
 

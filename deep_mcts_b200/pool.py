@@ -42,7 +42,8 @@ class TreePool:
     def __init__(self, manager: BoardManager, n_trees: int, max_nodes_per_tree: int = 1 << 16, seed: int = 0,
                  c_puct: float = 1.25, compaction: bool = True) -> None:
         """``compaction``: slide a tree's live subtree to the front of its arena at a re-root once the
-        arena is more than half full, so long games / long searches never outgrow ``max_nodes_per_tree``
+        arena may not hold the next move's search (or is half full, whichever comes first), so long games / long
+        searches never outgrow ``max_nodes_per_tree``
         as long as one move's search fits in half of it."""
         self.manager = manager
         self.n_trees = int(n_trees)

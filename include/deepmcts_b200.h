@@ -75,8 +75,8 @@ typedef struct {
     int32_t n_trees;             /* independent trees (games) in the pool */
     int32_t max_nodes_per_tree;  /* node arena per tree */
     int32_t device;              /* CUDA device ordinal */
-    int32_t compaction;          /* 1 = compact a tree's arena in place at a re-root when it is more than half
-                                    full (subtree reuse, mcts.py:105-108, without unbounded growth) */
+    int32_t compaction;          /* 1 = compact a tree's arena in place at a re-root when the next move's search
+                                    might not fit (subtree reuse, mcts.py:105-108, without unbounded growth) */
     double c_puct;               /* 1.25 in the reference (mcts.py:42) */
     uint64_t seed;               /* Philox key for device-side sampling */
 } dm_pool_config;
@@ -306,6 +306,11 @@ int dm_net_rollout_greedy(dm_net* net, int precision, int n, const uint64_t* fir
  * accumulated milliseconds and launch counts.  Used by bench.py for the roofline. */
 int dm_net_profile(dm_net* net, int enable);
 int dm_net_profile_read(dm_net* net, double ms_out[4], int64_t launches_out[4]);
+/* diagnostics: switch on per-warp timing of dm_pool_round and return the buffer it fills every launch,
+ * per_tree_dev[n_trees][4] = {cycles of the expand/backup phase, cycles of the selection phase,
+ * (moves << 32 | games << 24 | terminal simulations << 16 | levels walked), children scanned} of that launch.
+ * Used by scripts/tree_tail_probe.py to see which trees set a launch's duration. */
+int dm_pool_debug_timing(dm_pool* pool, uint64_t** per_tree_dev);
 /* number of kernel launches issued by this library since load (bench.py's gpu_launches) */
 uint64_t dm_launch_count(void);
 
