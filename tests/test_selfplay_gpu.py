@@ -231,3 +231,25 @@ def test_replay_window_in_games():
     starts = np.concatenate([[0], ends[:-1]])
     assert (first[starts] == 0).all() and (second[starts] == 0).all()
     assert pool.replay_window_start(10 ** 6) == 0
+
+
+def test_debug_timing_reports_every_warp():
+    """dm_pool_debug_timing (the diagnostic behind scripts/tree_tail_probe.py): after a self-play launch every tree
+    has non-zero cycle counts for the selection phase and a plausible level count."""
+    from deep_mcts_b200 import _lib
+    from deep_mcts_b200.pool import TreePool, wrap_device_buffer
+    manager = manager_for("othello", 6)
+    game = make_game("othello", 6)
+    pool = TreePool(manager, 64, 1 << 12, seed=1)
+    pool.configure(8, _lib.DM_EVAL_EXTERNAL, _lib.DM_ROLLOUT_NONE, 2, 0.5, 0.25)
+    pool.enable_selfplay(1 << 12)
+    ptr = _lib.c_void_p()
+    _lib.call("dm_pool_debug_timing", pool._h, ptr)
+    dbg = wrap_device_buffer(ptr.value, (64, 4), torch.int64, pool.device)
+    carry = {}
+    for _ in range(12):
+        host_round(pool, game, oev.hashed, carry)
+    torch.cuda.synchronize()
+    d = dbg.cpu().numpy()
+    assert (d[:, 1] > 0).all() and (d[:, 0] >= 0).all()
+    assert ((d[:, 2] & 0xffff) <= 128).all()
