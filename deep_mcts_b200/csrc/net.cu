@@ -49,6 +49,7 @@ struct dm_net {
     u8* r_player = nullptr;
     float *r_value = nullptr, *r_probs = nullptr;
     int* r_active = nullptr;
+    int* r_list[2] = {nullptr, nullptr};   // greedy rollouts: compacted lists of the boards still in play
     // optional CUDA-event timing per kernel class (0 encode+conv1, 1 tcgen05/fp32 trunk conv, 2 heads)
     bool prof = false;
     std::vector<cudaEvent_t> prof_events;  // pairs
@@ -128,9 +129,12 @@ void free_device(dm_net* net) {
     net->trunk_w16.clear();
 }
 
-// greedy rollout step: final states report their outcome and go inactive, others play argmax(probs)
-__global__ void k_greedy_step(GameCfg cfg, int n, u64* first, u64* second, u8* player, const float* probs,
-                              float* outcome, int* active) {
+// Greedy policy playouts (evaluate_complex_rollouts.py:57-59) keep a compacted list of the boards still in play: a
+// ply's network batch is exactly those boards (dm_net_evaluate_indexed semantics: board i of the batch is state
+// list[i], its priors land in row list[i]), finished boards cost nothing more.
+// init: final states report their outcome, the others enter the list
+__global__ void k_greedy_init(GameCfg cfg, int n, const u64* first, const u64* second, const u8* player, float* outcome,
+                              int* list, int* count) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     GState s;
@@ -138,15 +142,26 @@ __global__ void k_greedy_step(GameCfg cfg, int n, u64* first, u64* second, u8* p
     s.second = second[i];
     s.player = player[i];
     float o;
-    if (game_is_final(cfg, s, o)) {
-        outcome[i] = o;
-        return;
-    }
+    if (game_is_final(cfg, s, o)) outcome[i] = o;
+    else list[atomicAdd(count, 1)] = i;
+}
+
+// one ply: every listed board plays argmax(probs) (np.argmax: first maximum); boards that are still not final
+// enter the next list, finished ones report their outcome
+__global__ void k_greedy_step(GameCfg cfg, const int* count_in, const int* list_in, u64* first, u64* second, u8* player,
+                              const float* probs, float* outcome, int* list_out, int* count_out) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= *count_in) return;
+    const int i = list_in[k];
+    GState s;
+    s.first = first[i];
+    s.second = second[i];
+    s.player = player[i];
     const float* p = probs + (size_t)i * DM_MAX_ACTIONS;
     int best = 0;
     float bv = p[0];
     for (int a = 1; a < cfg.num_actions; ++a)
-        if (p[a] > bv) {  // np.argmax: first maximum
+        if (p[a] > bv) {
             bv = p[a];
             best = a;
         }
@@ -159,7 +174,9 @@ __global__ void k_greedy_step(GameCfg cfg, int n, u64* first, u64* second, u8* p
     first[i] = s.first;
     second[i] = s.second;
     player[i] = (u8)s.player;
-    atomicAdd(active, 1);
+    float o;
+    if (game_is_final(cfg, s, o)) outcome[i] = o;
+    else list_out[atomicAdd(count_out, 1)] = i;
 }
 
 int run_forward(dm_net* net, int precision, int n, const int* count_dev, const int* index, const u64* first,
@@ -402,6 +419,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
     DM_TRY(net_alloc_bytes(net, (void**)&net->r_value, (size_t)n * 4, false));
     DM_TRY(net_alloc_bytes(net, (void**)&net->r_probs, (size_t)n * DM_MAX_ACTIONS * 4, false));
     DM_TRY(net_alloc_bytes(net, (void**)&net->r_active, 16, true));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_list[0], (size_t)n * sizeof(int), false));
+    DM_TRY(net_alloc_bytes(net, (void**)&net->r_list[1], (size_t)n * sizeof(int), false));
     net->bf16_ready = false;
     if (C == netk::kC && R >= 1) {
         if ((int)net->trunk_w16.size() != L) net->trunk_w16.assign(L, nullptr);
@@ -572,19 +591,31 @@ extern "C" int dm_net_rollout_greedy(dm_net* net, int precision, int n, const ui
     DM_CUDA(cudaMemcpyAsync(net->r_first, first, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     DM_CUDA(cudaMemcpyAsync(net->r_second, second, (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     DM_CUDA(cudaMemcpyAsync(net->r_player, player, (size_t)n, cudaMemcpyDeviceToDevice, st));
+    // r_active = {count of list 0, count of list 1}; the lists alternate from ply to ply
+    int* counts = net->r_active;
+    DM_CUDA(cudaMemsetAsync(counts, 0, 2 * sizeof(int), st));
+    k_greedy_init<<<(n + 127) / 128, 128, 0, st>>>(net->game, n, net->r_first, net->r_second, net->r_player, outcome,
+                                                  net->r_list[0], counts);
+    DM_LAUNCH_CHECK();
     const int max_plies = 2 * net->game.cells + 4;
     for (int ply = 0; ply <= max_plies; ++ply) {
-        rc = run_forward(net, precision, n, nullptr, nullptr, net->r_first, net->r_second, net->r_player, 0,
+        const int cur = ply & 1, nxt = cur ^ 1;
+        // the boards still in play are the ply's whole batch; the host looks at their number only every fourth ply
+        // (an empty list makes every kernel of a ply return at once)
+        if ((ply & 3) == 0) {
+            int live = 0;
+            DM_CUDA(cudaMemcpyAsync(&live, counts + cur, sizeof(int), cudaMemcpyDeviceToHost, st));
+            DM_CUDA(cudaStreamSynchronize(st));
+            if (live == 0) return DM_OK;
+        }
+        rc = run_forward(net, precision, n, counts + cur, net->r_list[cur], net->r_first, net->r_second, net->r_player, 0,
                          net->r_value, net->r_probs, st);
         if (rc != DM_OK) return rc;
-        DM_CUDA(cudaMemsetAsync(net->r_active, 0, sizeof(int), st));
-        k_greedy_step<<<(n + 127) / 128, 128, 0, st>>>(net->game, n, net->r_first, net->r_second, net->r_player,
-                                                       net->r_probs, outcome, net->r_active);
+        DM_CUDA(cudaMemsetAsync(counts + nxt, 0, sizeof(int), st));
+        k_greedy_step<<<(n + 127) / 128, 128, 0, st>>>(net->game, counts + cur, net->r_list[cur], net->r_first,
+                                                       net->r_second, net->r_player, net->r_probs, outcome,
+                                                       net->r_list[nxt], counts + nxt);
         DM_LAUNCH_CHECK();
-        int active = 0;
-        DM_CUDA(cudaMemcpyAsync(&active, net->r_active, sizeof(int), cudaMemcpyDeviceToHost, st));
-        DM_CUDA(cudaStreamSynchronize(st));
-        if (active == 0) return DM_OK;
     }
     dm_set_error("dm_net_rollout_greedy: games did not finish");
     return DM_ERR_STATE;

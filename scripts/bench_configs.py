@@ -67,7 +67,7 @@ def rollouts(rank, world):
     torch.manual_seed(0)
     g = 7
     net = ConvolutionalHexWithSwapNet(g)
-    net.max_batch = 4096
+    net.max_batch = 8192
     manager = net.manager
     cases = [
         ("random rollouts, no evaluator (simple agent)", 4096, 400, dm.random_rollout_policy(manager), None),
@@ -75,6 +75,9 @@ def rollouts(rank, world):
         ("greedy policy-net rollouts, no evaluator (complex agent)", 2048, 20, dm.greedy_policy_rollout(net), None),
         ("greedy policy-net rollouts + network evaluator", 2048, 20, dm.greedy_policy_rollout(net),
          cached_state_evaluator(net)),
+        # a playout is ~40 sequential network batches over the boards still in play: more games per batch, not a
+        # faster kernel, is what raises this line
+        ("greedy policy-net rollouts, no evaluator (complex agent)", 8192, 20, dm.greedy_policy_rollout(net), None),
     ]
     for name, trees, sims, ro, ev in cases:
         m = dm.BatchedMCTS(manager, trees, sims, ro, ev, rollout_share=1.0, seed=rank)
