@@ -50,6 +50,7 @@ def parse_args():
     ap.add_argument("--pools", type=int, default=1, help="independent pools per GPU on separate streams")
     ap.add_argument("--pool-sizes", type=str, default="", help="comma-separated games per pool (default: even split)")
     ap.add_argument("--graph", type=int, default=1, help="1 = replay a captured CUDA graph of the round")
+    ap.add_argument("--max-nodes", type=int, default=0, help="node arena per tree (0 = the engine's default)")
     ap.add_argument("--ncu-rounds", type=int, default=0,
                     help="profiling aid: after the warm-up run this many rounds launch by launch inside a "
                          "cudaProfilerStart/Stop range (ncu --profile-from-start off) and exit")
@@ -276,7 +277,8 @@ def run_b200(args):
     engine = BatchedSelfPlay(net, T, sims, wl["sample_move_cutoff"], wl["dirichlet_alpha"], wl["dirichlet_factor"],
                              replay_capacity=1 << 20, seed=1000 + rank, n_pools=args.pools,
                              pool_sizes=[int(x) for x in args.pool_sizes.split(",")] if args.pool_sizes else None,
-                             eval_cache_log2=args.cache_log2 if args.cache_log2 > 0 else None)
+                             eval_cache_log2=args.cache_log2 if args.cache_log2 > 0 else None,
+                             max_nodes_per_tree=args.max_nodes or None)
     engine.use_graph = bool(args.graph)
     lib = _lib.load()
 
