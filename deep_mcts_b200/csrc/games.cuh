@@ -162,14 +162,27 @@ __device__ __forceinline__ u64 othello_flips_pp(u64 own, u64 opp, u64 bit, const
     return othello_flips_pp_inline(own, opp, bit, c);
 }
 
-// the empty square an own stone `bit` reaches over >=1 opponent stones in one direction,
-// else 0 (one iteration of the scan at othello/game.py:90-115)
+// Position of (dx, dy) in itertools.product([0, 1, -1], repeat=2) without the leading (0, 0): the order in which
+// legal_actions walks the rays of one stone (othello/game.py:89).
+__host__ __device__ constexpr int othello_dir_index(int dx, int dy) {
+    return (dx == 0 ? 0 : dx == 1 ? 3 : 6) + (dy == 0 ? 0 : dy == 1 ? 1 : 2) - 1;
+}
+
+// One direction seen from the EMPTY square `bit` (a legal move): the run of opponent stones next to it and the
+// own stone that brackets the run.  That stone is the one whose ray in the opposite direction reaches `bit` in
+// legal_actions' scan (othello/game.py:88-115), so the same walk yields the stones the move flips
+// (othello/game.py:56-81) and when the scan discovers the move: `seq` = 8 * stone cell + ray index, the position
+// of the (stone, ray) pair in the scan's loop order (stones ascending by cell, rays in product order).
 template <int DX, int DY>
-__device__ __forceinline__ u64 othello_ray_target(u64 own, u64 opp, u64 bit, const GameCfg& c) {
-    u64 f = bb_shift<DX, DY>(bit, c);
-    if (!(f & opp)) return 0;
-    while (f & opp) f = bb_shift<DX, DY>(f, c);
-    return f & ~(own | opp);
+__device__ __forceinline__ void othello_probe_dir(u64 own, u64 opp, u64 bit, const GameCfg& c, u64& flips, u32& seq) {
+    u64 t = bb_shift<DX, DY>(bit, c) & opp;
+    for (int i = 0; i < c.g - 3; ++i) t |= bb_shift<DX, DY>(t, c) & opp;
+    const u64 end = bb_shift<DX, DY>(t, c) & own;  // at most one bit: the square right behind the run
+    if (end) {
+        flips |= t;
+        const u32 q = ((u32)(__ffsll((long long)end) - 1) << 3) | (u32)othello_dir_index(-DX, -DY);
+        seq = min(seq, q);
+    }
 }
 
 // ---------------------------------------------------------------------------------- hex
@@ -332,45 +345,51 @@ struct WarpSet {
     int slot;  // this lane's slot (-1 empty)
     int size;  // 8 or 32
     int fill;
+    u32 occ;   // occupied slots (warp-uniform copy of "slot >= 0" per lane)
 
     __device__ __forceinline__ void init() {
         slot = -1;
         size = 8;
         fill = 0;
+        occ = 0;
     }
     __device__ __forceinline__ void place(int key, int lane) {
         u32 mask = (u32)size - 1u;
         u32 i = (u32)key & mask, perturb = (u32)key;
-        u32 empties = __ballot_sync(DM_FULL_MASK, slot < 0) & (size == 32 ? 0xffffffffu : 0xffu);
+        u32 empties = ~occ & (size == 32 ? 0xffffffffu : 0xffu);
         while (true) {
             u32 window = ((i + 9u <= mask) ? 0x3ffu : 1u) << i;  // LINEAR_PROBES = 9
             u32 hit = empties & window;
             if (hit) {
-                if (lane == __ffs(hit) - 1) slot = key;
+                const int target = __ffs(hit) - 1;
+                if (lane == target) slot = key;
+                occ |= 1u << target;
                 return;
             }
             perturb >>= 5;  // PERTURB_SHIFT
             i = (i * 5u + 1u + perturb) & mask;
         }
     }
-    // key must not be in the set yet (callers dedup with a bitmask)
+    // key must not be in the set yet (callers insert distinct keys)
     __device__ __forceinline__ void add(int key, int lane) {
         place(key, lane);
         ++fill;
         if (size == 8 && fill * 5 >= 21) {  // fill*5 >= mask*3 -> grow to 32 (4*5 = 20 < 32)
             int old = slot;
+            u32 old_occ = occ;
             slot = -1;
+            occ = 0;
             size = 32;
-            for (int s = 0; s < 8; ++s) {
-                int k = __shfl_sync(DM_FULL_MASK, old, s);
-                if (k >= 0) place(k, lane);
+            while (old_occ) {  // re-insert in slot order (set_table_resize walks the old table)
+                const int s = __ffs(old_occ) - 1;
+                old_occ &= old_occ - 1;
+                place(__shfl_sync(DM_FULL_MASK, old, s), lane);
             }
         }
     }
     // writes keys in slot order to out[0..fill)
     __device__ __forceinline__ void emit(u8* out, int lane) const {
-        u32 used = __ballot_sync(DM_FULL_MASK, slot >= 0);
-        if (slot >= 0) out[__popc(used & ((1u << lane) - 1u))] = (u8)slot;
+        if (slot >= 0) out[__popc(occ & ((1u << lane) - 1u))] = (u8)slot;
     }
 };
 
@@ -386,11 +405,15 @@ __device__ __forceinline__ void emit_ascending(u64 mask, bool extra, int extra_a
 // (iteration order of set(legal_actions(state)), mcts.py:200-215) to order_out[0..n) and,
 // if list_out != nullptr, the reference's legal_actions LIST order to list_out[0..n).
 // Both buffers need DM_MAX_ACTIONS + 1 bytes visible to the whole warp.  Returns n.
+// If `flips_out` is given and the Othello small-set path ran (warp-uniform `*have_flips`), lane p < n also
+// receives the stones flipped by the action order_out[p], a by-product of that path.
 __device__ __forceinline__ int warp_children_order(const GameCfg& c, const GState& s, int lane, u8* order_out,
-                                                   u8* list_out) {
+                                                   u8* list_out, u64* flips_out = nullptr,
+                                                   bool* have_flips = nullptr) {
     bool extra;
     u64 mask = game_legal_mask(c, s, extra);
     int n = __popcll(mask) + (extra ? 1 : 0);
+    if (have_flips) *have_flips = false;
     if (c.game == DM_OTHELLO && mask == 0) {  // only pass
         if (lane == 0) {
             order_out[0] = (u8)c.cells;
@@ -427,45 +450,37 @@ __device__ __forceinline__ int warp_children_order(const GameCfg& c, const GStat
         __syncwarp();
         return n;
     }
-    u64 own = s.player ? s.first : s.second, opp = s.player ? s.second : s.first;
+    const u64 own = s.player ? s.first : s.second, opp = s.player ? s.second : s.first;
+    // one legal move per lane (lane j < n: the j-th legal cell, ascending): every direction is walked from the
+    // move's square, which gives its flips and the first (stone, ray) pair of the reference's scan that finds it
+    emit_ascending(mask, false, c.cells, order_out, lane);
+    __syncwarp();
+    const int cell = order_out[lane < n ? lane : 0];
+    __syncwarp();
+    u64 flips = 0;
+    u32 seq = 0xffffffffu;
+    {
+        const u64 bit = 1ull << cell;
+#define DM_DIR(DX, DY) othello_probe_dir<DX, DY>(own, opp, bit, c, flips, seq);
+        DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
+#undef DM_DIR
+    }
+    if (lane >= n) seq = 0xffffffffu;
+    // the scan adds a move when it first meets it: rank the moves by that moment (all seq are distinct)
+    int rank = 0;
+    for (int i = 0; i < n; ++i) rank += (__shfl_sync(DM_FULL_MASK, seq, i) < seq) ? 1 : 0;
+    if (lane < n) order_out[rank] = (u8)cell;
+    __syncwarp();
+    const int discovered = order_out[lane < n ? lane : 0];  // lane r: the r-th move the scan adds to its set
+    __syncwarp();
     WarpSet stage1;
     stage1.init();
-    u64 seen = 0;
-    for (int half = 0; half < 2; ++half) {
-        int cell = lane + 32 * half;
-        u64 packed = ~0ull;  // 8 target bytes, 0xff = none
-        if (cell < c.cells && ((own >> cell) & 1)) {
-            u64 bit = 1ull << cell;
-            int d = 0;
-#define DM_DIR(DX, DY)                                                                                   \
-    {                                                                                                    \
-        u64 t = othello_ray_target<DX, DY>(own, opp, bit, c);                                            \
-        if (t) packed = (packed & ~(0xffull << (8 * d))) | ((u64)(__ffsll((long long)t) - 1) << (8 * d)); \
-        ++d;                                                                                             \
-    }
-            DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
-#undef DM_DIR
-        }
-        u32 active = __ballot_sync(DM_FULL_MASK, packed != ~0ull);
-        while (active) {
-            int src = __ffs(active) - 1;
-            active &= active - 1;
-            u64 p = __shfl_sync(DM_FULL_MASK, packed, src);
-#pragma unroll
-            for (int d = 0; d < 8; ++d) {
-                int k = (int)((p >> (8 * d)) & 0xff);
-                if (k != 0xff && !((seen >> k) & 1)) {
-                    seen |= 1ull << k;
-                    stage1.add(k, lane);
-                }
-            }
-        }
-    }
+    for (int r = 0; r < n; ++r) stage1.add(__shfl_sync(DM_FULL_MASK, discovered, r), lane);
+    if (list_out) stage1.emit(list_out, lane);
     // second set: insert stage-1 keys in stage-1 slot order
     WarpSet stage2;
     stage2.init();
-    u32 used = __ballot_sync(DM_FULL_MASK, stage1.slot >= 0);
-    if (list_out) stage1.emit(list_out, lane);
+    u32 used = stage1.occ;
     while (used) {
         int src = __ffs(used) - 1;
         used &= used - 1;
@@ -473,6 +488,13 @@ __device__ __forceinline__ int warp_children_order(const GameCfg& c, const GStat
     }
     stage2.emit(order_out, lane);
     __syncwarp();
+    if (flips_out) {
+        // lane p takes the flips of the move at child position p from the lane that walked it
+        const int a = order_out[lane < n ? lane : 0];
+        const int src = __popcll(mask & ((1ull << a) - 1ull));
+        *flips_out = __shfl_sync(DM_FULL_MASK, flips, src);
+        if (have_flips) *have_flips = true;
+    }
     return n;
 }
 

@@ -531,7 +531,9 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
                                        int eval_kind, const float* ext_f32, const double* ext_f64,
                                        double& eval_value) {
     const size_t base = (size_t)t * P.cap;
-    int n = warp_children_order(P.cfg, s, lane, s_order, nullptr);
+    u64 flips = 0;
+    bool have_flips = false;  // Othello: the child order's small-set path already walked every move's rays
+    int n = warp_children_order(P.cfg, s, lane, s_order, nullptr, &flips, &have_flips);
     u32 cnt = P.node_count[t];
     if (cnt + (u32)n > P.cap) {
         if (lane == 0) count(P, kCntCapacity, 1);
@@ -563,7 +565,15 @@ __device__ __forceinline__ bool expand(const PoolView& P, int t, int lane, u32 n
         P.first_child[c] = 0;
         P.n_children[c] = 0;
         P.action[c] = (u8)a;
-        const GState child = game_child_uniform(P.cfg, s, a);
+        GState child;
+        if (have_flips) {  // n <= 18: one pass of this loop, flips belong to s_order[lane]
+            const u64 bit = 1ull << a;
+            child.player = 1 - s.player;
+            child.first = s.player ? (s.first | bit | flips) : (s.first & ~flips);
+            child.second = s.player ? (s.second & ~flips) : (s.second | bit | flips);
+        } else {
+            child = game_child_uniform(P.cfg, s, a);
+        }
         P.node_first[c] = child.first;
         P.node_second[c] = child.second;
         P.node_final[c] = (u8)game_child_final_code(P.cfg, s, a, child);
