@@ -401,6 +401,23 @@ __device__ __forceinline__ void emit_ascending(u64 mask, bool extra, int extra_a
     if (extra && lane == 0) out[__popcll(mask)] = (u8)extra_action;
 }
 
+// A set of 5..18 distinct keys < 64 no two of which agree modulo 32 sits in a 32-slot table with every key in its
+// home slot (key & 31) whatever the insertion order was -- the 8-slot phase included, its keys are re-inserted into
+// the 32-slot table when the fifth key arrives -- so the set iterates in ascending key & 31.  `keys` has bit k set
+// for key k; lo & hi == 0 is exactly "no two keys share a home slot".
+__device__ __forceinline__ bool set_order_is_by_home_slot(u64 keys, int n) {
+    return n >= 5 && n <= 18 && ((u32)keys & (u32)(keys >> 32)) == 0;
+}
+__device__ __forceinline__ void emit_by_home_slot(u64 keys, u8* out, u8* out2, int lane) {
+    const u32 lo = (u32)keys, hi = (u32)(keys >> 32), any = lo | hi;
+    if ((any >> lane) & 1) {
+        const int pos = __popc(any & ((1u << lane) - 1u));
+        const u8 key = (u8)(((lo >> lane) & 1) ? lane : lane + 32);
+        out[pos] = key;
+        if (out2) out2[pos] = key;
+    }
+}
+
 // Warp-cooperative.  Writes the order in which MCTS.expand_node creates children
 // (iteration order of set(legal_actions(state)), mcts.py:200-215) to order_out[0..n) and,
 // if list_out != nullptr, the reference's legal_actions LIST order to list_out[0..n).
@@ -425,8 +442,11 @@ __device__ __forceinline__ int warp_children_order(const GameCfg& c, const GStat
     if (c.game != DM_OTHELLO) {
         // legal_actions is the ascending list (+ swap last); children = set(list)
         if (list_out) emit_ascending(mask, extra, c.cells, list_out, lane);
+        const u64 keys = mask | ((extra && c.cells < 64) ? (1ull << c.cells) : 0ull);
         if (n >= 19) {
             emit_ascending(mask, extra, c.cells, order_out, lane);
+        } else if (!(extra && c.cells >= 64) && set_order_is_by_home_slot(keys, n)) {
+            emit_by_home_slot(keys, order_out, nullptr, lane);
         } else {
             WarpSet set;
             set.init();
@@ -465,28 +485,34 @@ __device__ __forceinline__ int warp_children_order(const GameCfg& c, const GStat
         DM_FOR_EACH_OTHELLO_DIR(DM_DIR)
 #undef DM_DIR
     }
-    if (lane >= n) seq = 0xffffffffu;
-    // the scan adds a move when it first meets it: rank the moves by that moment (all seq are distinct)
-    int rank = 0;
-    for (int i = 0; i < n; ++i) rank += (__shfl_sync(DM_FULL_MASK, seq, i) < seq) ? 1 : 0;
-    if (lane < n) order_out[rank] = (u8)cell;
-    __syncwarp();
-    const int discovered = order_out[lane < n ? lane : 0];  // lane r: the r-th move the scan adds to its set
-    __syncwarp();
-    WarpSet stage1;
-    stage1.init();
-    for (int r = 0; r < n; ++r) stage1.add(__shfl_sync(DM_FULL_MASK, discovered, r), lane);
-    if (list_out) stage1.emit(list_out, lane);
-    // second set: insert stage-1 keys in stage-1 slot order
-    WarpSet stage2;
-    stage2.init();
-    u32 used = stage1.occ;
-    while (used) {
-        int src = __ffs(used) - 1;
-        used &= used - 1;
-        stage2.add(__shfl_sync(DM_FULL_MASK, stage1.slot, src), lane);
+    if (set_order_is_by_home_slot(mask, n)) {
+        // no two moves share a home slot: the scan's set and expand_node's set both iterate by key & 31,
+        // in whatever order the scan met the moves
+        emit_by_home_slot(mask, order_out, list_out, lane);
+    } else {
+        if (lane >= n) seq = 0xffffffffu;
+        // the scan adds a move when it first meets it: rank the moves by that moment (all seq are distinct)
+        int rank = 0;
+        for (int i = 0; i < n; ++i) rank += (__shfl_sync(DM_FULL_MASK, seq, i) < seq) ? 1 : 0;
+        if (lane < n) order_out[rank] = (u8)cell;
+        __syncwarp();
+        const int discovered = order_out[lane < n ? lane : 0];  // lane r: the r-th move the scan adds to its set
+        __syncwarp();
+        WarpSet stage1;
+        stage1.init();
+        for (int r = 0; r < n; ++r) stage1.add(__shfl_sync(DM_FULL_MASK, discovered, r), lane);
+        if (list_out) stage1.emit(list_out, lane);
+        // second set: insert stage-1 keys in stage-1 slot order
+        WarpSet stage2;
+        stage2.init();
+        u32 used = stage1.occ;
+        while (used) {
+            int src = __ffs(used) - 1;
+            used &= used - 1;
+            stage2.add(__shfl_sync(DM_FULL_MASK, stage1.slot, src), lane);
+        }
+        stage2.emit(order_out, lane);
     }
-    stage2.emit(order_out, lane);
     __syncwarp();
     if (flips_out) {
         // lane p takes the flips of the move at child position p from the lane that walked it

@@ -1387,7 +1387,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32, 7)
             s.first = P.pend_first[t];
             s.second = P.pend_second[t];
             s.player = P.pend_player[t];
-            expand_backup_tree<PriorT>(P, t, P.pend_slot[t], lane, s, P.pend_flags[t], s_order[warp], priors, stride, values);
+            const int slot = P.pend_slot[t];
+            const u8 leaf_flag = P.pend_flags[t];
+            expand_backup_tree<PriorT>(P, t, slot, lane, s, leaf_flag, s_order[warp], priors, stride, values);
         }
         const long long t1 = P.dbg_warp ? clock64() : 0;
         select_tree<kSelfPlay, kSelfPlay>(P, t, lane, s_path[warp], now);
