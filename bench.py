@@ -379,7 +379,7 @@ def run_b200(args):
         visits, stats = searcher.step()                           # D2H: visit counts + statistics
         # the host chooses the moves like MCTS.self_play (mcts.py:99-104): sampled in proportion to the visit counts
         # for the first sample_move_cutoff plies of a game, argmax (first maximum) afterwards
-        actions = visits.argmax(axis=1)
+        actions = torch.from_numpy(visits).argmax(dim=1).numpy()   # first maximum, like np.argmax; uses the host's cores
         early = np.where(h_ply < wl["sample_move_cutoff"])[0]
         if early.size:
             cdf = np.cumsum(visits[early].astype(np.float64), axis=1)

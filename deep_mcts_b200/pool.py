@@ -72,8 +72,17 @@ class TreePool:
         self.leaf_index = wrap_device_buffer(idx.value, (T,), torch.int32, self.device)
         self.cache_entries = 0
         self.dense_batch = False    # the pending leaf batch is dense (slot = tree) and must be read through leaf_index
-        self._visits = torch.zeros((T, _lib.DM_MAX_ACTIONS), dtype=torch.int32, device=self.device)
-        self._stats = torch.zeros((T, 2), dtype=torch.int32, device=self.device)
+        # read-out staging: ONE device buffer per call and a pinned host mirror, so a read-out is one kernel, one
+        # asynchronous copy and one stream synchronisation (visits | stats; first | second | outcome | player | final)
+        A = _lib.DM_MAX_ACTIONS
+        self._visit_words = T * A + T * 2
+        self._visit_buf = torch.zeros(self._visit_words, dtype=torch.int32, device=self.device)
+        self._visits = self._visit_buf[: T * A].view(T, A)
+        self._stats = self._visit_buf[T * A:].view(T, 2)
+        self._state_buf = torch.zeros(T * 22, dtype=torch.uint8, device=self.device)
+        self._actions_dev = torch.zeros(T, dtype=torch.int32, device=self.device)
+        self._h_visit_buf = self._h_state_buf = self._h_actions = None
+        self._actions_copied = None
 
     def close(self) -> None:
         if getattr(self, "_h", None) is not None and self._h.value:
@@ -233,10 +242,17 @@ class TreePool:
     # -------------------------------------------------------------------------- read-out
     def root_visits(self) -> Tuple[np.ndarray, np.ndarray]:
         """(visits[n_trees, num_actions], stats[n_trees, 2]) of the last step (mcts.py:139-148)."""
+        T, A = self.n_trees, _lib.DM_MAX_ACTIONS
+        if self._h_visit_buf is None:
+            self._h_visit_buf = torch.empty(self._visit_words, dtype=torch.int32, pin_memory=True)
         with torch.cuda.device(self.device):
             _lib.call("dm_pool_root_visits", self._h, self._visits.data_ptr(), self._stats.data_ptr(),
                       self._stream())
-        return self._visits[:, : self.num_actions].cpu().numpy(), self._stats.cpu().numpy()
+            self._h_visit_buf.copy_(self._visit_buf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        host = self._h_visit_buf.numpy()
+        # copies: the pinned mirror is overwritten by the next read-out
+        return host[: T * A].reshape(T, A)[:, : self.num_actions].copy(), host[T * A:].reshape(T, 2).copy()
 
     def root_children(self) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
         T = self.n_trees
@@ -259,24 +275,34 @@ class TreePool:
         return prior.cpu().numpy(), vsum.cpu().numpy()
 
     def advance(self, actions) -> None:
-        a = torch.from_numpy(np.asarray(actions, dtype=np.int32)).to(self.device)
-        assert a.numel() == self.n_trees
+        a = np.asarray(actions, dtype=np.int32).reshape(-1)
+        assert a.size == self.n_trees
+        if self._h_actions is None:
+            self._h_actions = torch.empty(self.n_trees, dtype=torch.int32, pin_memory=True)
+            self._actions_copied = torch.cuda.Event()
+        else:
+            self._actions_copied.synchronize()      # the previous upload has left the pinned staging buffer
+        self._h_actions.numpy()[:] = a
         with torch.cuda.device(self.device):
-            _lib.call("dm_pool_advance", self._h, a.data_ptr(), self._stream())
+            self._actions_dev.copy_(self._h_actions, non_blocking=True)
+            self._actions_copied.record()
+            _lib.call("dm_pool_advance", self._h, self._actions_dev.data_ptr(), self._stream())
 
     def states(self):
         """(player, first, second, is_final, outcome) numpy arrays of the current roots."""
         T = self.n_trees
-        f = torch.empty(T, dtype=torch.int64, device=self.device)
-        s = torch.empty(T, dtype=torch.int64, device=self.device)
-        p = torch.empty(T, dtype=torch.uint8, device=self.device)
-        fin = torch.empty(T, dtype=torch.uint8, device=self.device)
-        out = torch.empty(T, dtype=torch.float32, device=self.device)
+        if self._h_state_buf is None:
+            self._h_state_buf = torch.empty(T * 22, dtype=torch.uint8, pin_memory=True)
+        base = self._state_buf.data_ptr()       # first | second (8 B each) | outcome (4 B) | player | final (1 B each)
         with torch.cuda.device(self.device):
-            _lib.call("dm_pool_states", self._h, f.data_ptr(), s.data_ptr(), p.data_ptr(), fin.data_ptr(),
-                      out.data_ptr(), self._stream())
-        return (p.cpu().numpy(), f.cpu().numpy().view(np.uint64), s.cpu().numpy().view(np.uint64),
-                fin.cpu().numpy().astype(bool), out.cpu().numpy())
+            _lib.call("dm_pool_states", self._h, base, base + 8 * T, base + 20 * T, base + 21 * T, base + 16 * T,
+                      self._stream())
+            self._h_state_buf.copy_(self._state_buf, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        host = self._h_state_buf.numpy()
+        return (host[20 * T: 21 * T].copy(), host[: 8 * T].view(np.uint64).copy(),
+                host[8 * T: 16 * T].view(np.uint64).copy(), host[21 * T: 22 * T].astype(bool),
+                host[16 * T: 20 * T].view(np.float32).copy())
 
     COUNTER_NAMES = ("simulations", "leaf_evals", "terminal_sims", "nodes_high_water", "games", "depth_sum",
                      "children_scanned", "children_created", "capacity_errors", "moves", "rollout_plies",

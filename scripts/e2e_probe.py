@@ -54,7 +54,7 @@ def main():
         return out
 
     def choose(visits):
-        actions = visits.argmax(axis=1)
+        actions = torch.from_numpy(visits).argmax(dim=1).numpy()
         early = np.where(h_ply < cutoff)[0]
         if early.size:
             cdf = np.cumsum(visits[early].astype(np.float64), axis=1)
