@@ -1295,7 +1295,7 @@ __global__ void __launch_bounds__(kFcThreads, 1) k_policy_fc_tc(FcArgs args) {
 constexpr int kFinishBoards = 16;
 // GAME >= 0: instantiated for one (game, board size), so the legality mask's bitboard code has constant shifts.
 template <int GAME, int G>
-__global__ void __launch_bounds__(kFinishBoards * 32) k_heads_finish(GameCfg cfg_in, int n, const int* count_dev, const int* index,
+__global__ void __launch_bounds__(kFinishBoards * 32, 2) k_heads_finish(GameCfg cfg_in, int n, const int* count_dev, const int* index,
                                                       const u64* first,
                                                       const u64* second, const u8* player,
                                                       const float* __restrict__ partial, int split, int n_cap, int NA,
