@@ -27,6 +27,9 @@ struct dm_net {
     // fp32 weights
     float *conv1_w = nullptr, *conv1_b = nullptr;
     __half* conv1_tab16 = nullptr;  // k_encode_conv1_table operand: padded fp16 table image
+    __nv_bfloat16* stem_w16 = nullptr;  // k_stem_tc B operand: [8 K-chunks (hi 0-3, lo 4-7)][128][8]
+    std::vector<float> h_conv1_b;       // folded first-layer bias (passed by value to k_stem_tc)
+    bool stem_table = false;            // DM_STEM_TABLE=1 selects the table kernel for the first layer (A/B testing)
     std::vector<float*> trunk_w, trunk_b;
     float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_t = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
     float vconv_b = 0.f, vfc2_b = 0.f;
@@ -223,11 +226,22 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const i
         return DM_ERR_INVALID;
     }
     int pe = prof_begin(net, 0, st);
-    const int enc3_groups = (n + netk::kEncode3Boards - 1) / netk::kEncode3Boards;
-    const int enc3_blocks = std::min(enc3_groups, netk::kEncode3CtasPerSm * net->sm_count);
-    netk::k_encode_conv1_table<<<enc3_blocks, 256, netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, index, first, second, player,
-                                                                         net->conv1_tab16, C, net->a0,
-                                                                         net->rows_total, net->pair_layout ? 1 : 0);
+    if (net->stem_table) {
+        const int enc3_groups = (n + netk::kEncode3Boards - 1) / netk::kEncode3Boards;
+        const int enc3_blocks = std::min(enc3_groups, netk::kEncode3CtasPerSm * net->sm_count);
+        netk::k_encode_conv1_table<<<enc3_blocks, 256, netk::encode3_smem_bytes(C, g.g), st>>>(g, n, count_dev, index, first, second, player,
+                                                                             net->conv1_tab16, C, net->a0,
+                                                                             net->rows_total, net->pair_layout ? 1 : 0);
+    } else {
+        netk::StemArgs sa;
+        sa.cfg = g; sa.n = n; sa.count_dev = count_dev; sa.index = index; sa.first = first; sa.second = second;
+        sa.player = player; sa.w = net->stem_w16; sa.out = net->a0; sa.rows_total = net->rows_total;
+        sa.pair_layout = net->pair_layout ? 1 : 0;
+        memcpy(sa.bias_c, net->h_conv1_b.data(), sizeof(sa.bias_c));
+        const int stem_items = (n + 1) / 2;
+        const int stem_blocks = std::min(stem_items, netk::kStemCtasPerSm * net->sm_count);
+        netk::k_stem_tc<<<stem_blocks, netk::kStemThreads, netk::stem_smem_bytes(), st>>>(sa);
+    }
     prof_end(net, pe, st);
     DM_LAUNCH_CHECK();
     const bool v1 = net->conv_v1, pair = net->pair_layout;
@@ -465,6 +479,20 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
             for (int r = 0; r < 32; ++r)
                 for (int c = 0; c < C; ++c) tab16[(size_t)(81 + r) * CP + c] = __float2half_rn(basev[(size_t)r * C + c]);
             DM_TRY(net_upload(net, &net->conv1_tab16, tab16));
+            // the same layer as a tcgen05 B operand: k = tap * 3 + plane (27 of 32 rows), hi part then lo part
+            std::vector<__nv_bfloat16> sw((size_t)8 * C * 8, __float2bfloat16(0.f));
+            for (int k = 0; k < 27; ++k)
+                for (int c = 0; c < C; ++c) {
+                    const float w = hw.conv1_w[(size_t)k * C + c];
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+                    sw[((size_t)(k >> 3) * C + c) * 8 + (k & 7)] = hi;
+                    sw[((size_t)(4 + (k >> 3)) * C + c) * 8 + (k & 7)] = lo;
+                }
+            DM_TRY(net_upload(net, &net->stem_w16, sw));
+            net->h_conv1_b = hw.conv1_b;
+            const char* st_env = getenv("DM_STEM_TABLE");
+            net->stem_table = st_env && st_env[0] == '1';
             DM_CUDA(cudaFuncSetAttribute(netk::k_encode_conv1_table, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)netk::encode3_smem_bytes(C, g)));
         }

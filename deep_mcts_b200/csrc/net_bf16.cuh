@@ -539,6 +539,200 @@ __global__ void __launch_bounds__(256) k_encode_conv1_table(GameCfg cfg, int n, 
     if (!tables_ready) mbar_wait(bar, 0);   // never leave with the bulk copy in flight
 }
 
+// ============================================================================================
+// The same first layer on the tensor cores (the one the engine runs; the table kernel above stays selectable with
+// DM_STEM_TABLE=1 as its A/B baseline).  A cell's 3x3 window over the three input planes is 27 numbers that are 0 or
+// 1, so the layer is a [cells x 27] x [27 x 128] GEMM whose A rows the kernel writes itself, straight from the
+// bitboards, into the K-major / no-swizzle operand layout (no gather, no tables): one thread per cell builds its
+// row (27 bf16 ones/zeros padded to 32 = four 16-byte chunks), one tcgen05.mma group multiplies 128 cells (two
+// boards) by the folded weights, and the same 128 threads drain the accumulator (+bias, ReLU, bf16) into the
+// trunk's activation layout.  The weights are split hi + lo (w = bf16(w) + bf16(w - bf16(w))): the B operand has
+// K = 64 with both halves, the A descriptor of the lo half simply points at the same rows, so the products are exact
+// to 2^-17 relative -- tighter than the fp16 tables of the kernel above -- at no extra operand traffic.
+// Per board: ~0.3 k warp instructions for the rows + ~0.7 k for the epilogue (table kernel: 3.2 k), no
+// shared-memory bandwidth to speak of; what is left is the 16 KB per board of activation writes.
+constexpr int kStemThreads = 128;                 // one thread per GEMM row = TMEM lane
+constexpr int kStemCtasPerSm = 4;                 // 4 x 128 TMEM columns
+constexpr int kStemABytes = 4 * kTileM * 16;      // 4 K-chunks x 128 rows x 16 B
+constexpr int kStemBBytes = 8 * kC * 16;          // 8 K-chunks (hi 0-3, lo 4-7) x 128 couts x 16 B
+inline size_t stem_smem_bytes() { return 1024 + kStemABytes + kStemBBytes + 64; }
+
+struct StemArgs {
+    GameCfg cfg;
+    int n;
+    const int* count_dev;
+    const int* index;
+    const u64* first;
+    const u64* second;
+    const u8* player;
+    const __nv_bfloat16* w;   // [8][128][8]: k = tap * 3 + plane (27 of 32), hi then lo
+    __nv_bfloat16* out;       // trunk activation rows
+    size_t rows_total;
+    int pair_layout;
+    float bias_c[128];        // folded bias, by value (constant bank)
+};
+
+__global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) k_stem_tc(StemArgs args) {
+    extern __shared__ unsigned char smem_raw[];
+    const GameCfg cfg = args.cfg;
+    const int g = cfg.g, P0 = g * g;
+    const int live = live_count(args.count_dev, args.n);
+    const int n_items = (live + 1) / 2;           // one item = one MMA tile = two boards
+    if ((int)blockIdx.x >= n_items) return;
+    unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
+    unsigned char* s_a = base;
+    unsigned char* s_b = s_a + kStemABytes;
+    u64* s_bar = (u64*)(s_b + kStemBBytes);       // weights arrived, accumulator ready
+    u32* s_tmem = (u32*)(s_bar + 2);
+    const u32 bar_w = smem_u32(&s_bar[0]), bar_acc = smem_u32(&s_bar[1]);
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int r = threadIdx.x;                    // GEMM row of this thread
+    if (threadIdx.x == 0) {
+        mbar_init(bar_w, 1);
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(bar_w, kStemBBytes);
+        bulk_g2s(smem_u32(s_b), args.w, kStemBBytes, bar_w);
+    }
+    __syncwarp();
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(s_tmem)),
+                     "r"(128)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const u32 tmem_base = *s_tmem;
+
+    // this thread's cell: board (r >> 6) of the item, cell r & 63 in the net's own coordinates
+    const int b2 = r >> 6, c = r & 63;
+    const bool real = c < P0;
+    const int y = real ? c / g : 0, x = real ? c % g : 0;
+    const bool hex_like = (cfg.game == DM_HEX || cfg.game == DM_HEX_SWAP);
+    const RowGeom geom = RowGeom::make(g);
+    bool weights_ready = false;
+    int j = 0;
+    // index -> state is a chain of two dependent loads: the state of item j+1 and the index of item j+2 are
+    // requested while item j is worked on, so neither is ever waited for inside the loop
+    const int stride = (int)gridDim.x;
+    auto state_index = [&](int item) -> int {
+        const int b = 2 * item + b2;
+        if (!real || item >= n_items || b >= live) return -1;
+        return args.index ? args.index[b] : b;   // board b of the batch is state index[b]
+    };
+    int src_next = state_index((int)blockIdx.x + stride);
+    u64 nf = 0, ns = 0;
+    int npl = 0;
+    {
+        const int src = state_index((int)blockIdx.x);
+        if (src >= 0) {
+            nf = args.first[src];
+            ns = args.second[src];
+            npl = args.player[src];
+        }
+    }
+    for (int it = blockIdx.x; it < n_items; it += stride, ++j) {
+        const int b = 2 * it + b2;
+        const bool valid = real && b < live;
+        const u64 f = nf, s2 = ns;
+        const int pl = npl;
+        if (src_next >= 0) {
+            nf = args.first[src_next];
+            ns = args.second[src_next];
+            npl = args.player[src_next];
+        }
+        src_next = state_index(it + 2 * stride);
+        u32 w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = 0;
+        if (valid) {
+            const u64 own = pl ? f : s2, opp = pl ? s2 : f;
+            const bool transpose = hex_like && pl == 0;       // Hex nets see the transposed board when SECOND moves
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+                const int ny = y + tap / 3 - 1, nx = x + tap % 3 - 1;
+                if (ny < 0 || ny >= g || nx < 0 || nx >= g) continue;   // zero padding
+                const int bit = transpose ? nx * g + ny : ny * g + nx;
+                const u32 in[3] = {(u32)((own >> bit) & 1), (u32)((opp >> bit) & 1), (u32)pl};
+#pragma unroll
+                for (int plane = 0; plane < 3; ++plane) {
+                    const int k = tap * 3 + plane;            // bf16 1.0 = 0x3f80 in half (k & 1) of word k / 2
+                    w[k >> 1] |= in[plane] * ((k & 1) ? 0x3f800000u : 0x00003f80u);
+                }
+            }
+        }
+#pragma unroll
+        for (int kc = 0; kc < 4; ++kc)
+            *reinterpret_cast<uint4*>(s_a + ((size_t)kc * kTileM + r) * 16) =
+                make_uint4(w[4 * kc], w[4 * kc + 1], w[4 * kc + 2], w[4 * kc + 3]);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor core
+        __syncthreads();
+        if (warp == 0) {
+            if (!weights_ready) {
+                mbar_wait(bar_w, 0);
+                weights_ready = true;
+            }
+            tc_fence_after();
+            if (elect_one()) {
+                const u32 lbo = kTileM * 16, sbo = 128;
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                    const u64 ad = umma_desc(smem_u32(s_a) + (u32)((k16 & 1) * 2) * lbo, lbo, sbo);   // lo half re-reads the rows
+                    const u64 bd = umma_desc(smem_u32(s_b) + (u32)(k16 * 2) * (u32)(kC * 16), kC * 16, sbo);
+                    tc_mma_bf16(tmem_base, ad, bd, kIdescBf16, k16 ? 1u : 0u);
+                }
+                tc_commit(bar_acc);
+            }
+            __syncwarp();
+        }
+        mbar_wait(bar_acc, j & 1);
+        tc_fence_after();
+        const size_t row = args.pair_layout ? pair_entry(b, y, x)
+                                            : (size_t)geom.halo + (size_t)b * geom.P + y * geom.Wp + x;
+        // two register buffers: the TMEM load of columns cc+1 is in flight while columns cc are converted and stored
+        u32 va[32], vb[32];
+        const u32 taddr = tmem_base + ((u32)(warp * 32) << 16);
+        auto emit = [&](const u32 (&v)[32], int cc) {
+            if (!valid) return;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+                float o[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                    o[jj] = fmaxf(__uint_as_float(v[c4 * 8 + jj]) + args.bias_c[cc * 32 + c4 * 8 + jj], 0.f);
+                uint4 q;
+                q.x = pack_bf16(o[0], o[1]);
+                q.y = pack_bf16(o[2], o[3]);
+                q.z = pack_bf16(o[4], o[5]);
+                q.w = pack_bf16(o[6], o[7]);
+                *reinterpret_cast<uint4*>(args.out + ((size_t)(cc * 4 + c4) * args.rows_total + row) * 8) = q;
+            }
+        };
+        tc_ld32(taddr, va);
+        tc_wait_ld();
+        tc_ld32(taddr + 32, vb);
+        emit(va, 0);
+        tc_wait_ld();
+        tc_ld32(taddr + 64, va);
+        emit(vb, 1);
+        tc_wait_ld();
+        tc_ld32(taddr + 96, vb);
+        emit(va, 2);
+        tc_wait_ld();
+        emit(vb, 3);
+        tc_fence_before();
+        __syncthreads();   // rows and accumulator are free for the next item
+    }
+    if (!weights_ready && warp == 0) mbar_wait(bar_w, 0);   // never leave with the bulk copy in flight
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(128) : "memory");
+    }
+}
+
 template <bool kPair>
 __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args) {
     extern __shared__ unsigned char smem_raw[];
