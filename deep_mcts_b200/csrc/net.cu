@@ -30,6 +30,7 @@ struct dm_net {
     __nv_bfloat16* stem_w16 = nullptr;  // k_stem_tc B operand: [8 K-chunks (hi 0-3, lo 4-7)][128][8]
     std::vector<float> h_conv1_b;       // folded first-layer bias (passed by value to k_stem_tc)
     bool stem_table = false;            // DM_STEM_TABLE=1 selects the table kernel for the first layer (A/B testing)
+    int trunk_cluster = 2;              // fused trunk kernel as 2-CTA clusters with multicast weights; DM_TRUNK_CLUSTER=1: single CTAs (A/B)
     std::vector<float*> trunk_w, trunk_b;
     float *vconv_w = nullptr, *vfc1_w = nullptr, *vfc1_t = nullptr, *vfc1_b = nullptr, *vfc2_w = nullptr, *pfc_w = nullptr, *pfc_b = nullptr;
     float vconv_b = 0.f, vfc2_b = 0.f;
@@ -281,10 +282,20 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const i
                 memcpy(ra.vw_c, net->h_vconv_w.data(), sizeof(ra.vw_c));
             }
             int pc = prof_begin(net, 1, st);
-            if (g.g == 8)
-                netk::k_resblock_tc<8><<<conv_blocks, netk::kConv2Threads, netk::resblock_smem_bytes<8>(), st>>>(ra);
-            else
-                netk::k_resblock_tc<7><<<conv_blocks, netk::kConv2Threads, netk::resblock_smem_bytes<7>(), st>>>(ra);
+            // clusters of CL CTAs sharing the weight stream need a grid and an item capacity that are multiples of CL
+            int cl = net->trunk_cluster;
+            while (cl > 1 && (conv_blocks < cl || (conv_items % cl) != 0)) cl >>= 1;
+            const int cblocks = conv_blocks / cl * cl;
+            const size_t rsm = g.g == 8 ? netk::resblock_smem_bytes<8>() : netk::resblock_smem_bytes<7>();
+#define DM_RESBLOCK(G, CL) netk::k_resblock_tc<G, CL><<<cblocks, netk::kConv2Threads, rsm, st>>>(ra)
+            if (g.g == 8) {
+                if (cl == 2) DM_RESBLOCK(8, 2);
+                else DM_RESBLOCK(8, 1);
+            } else {
+                if (cl == 2) DM_RESBLOCK(7, 2);
+                else DM_RESBLOCK(7, 1);
+            }
+#undef DM_RESBLOCK
             prof_end(net, pc, st);
             DM_LAUNCH_CHECK();
         }
@@ -541,6 +552,14 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
                                      (int)netk::resblock_smem_bytes<8>()));
         DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::resblock_smem_bytes<7>()));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::resblock_smem_bytes<8>()));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<7, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::resblock_smem_bytes<7>()));
+        {
+            const char* cl = getenv("DM_TRUNK_CLUSTER");
+            net->trunk_cluster = (cl && cl[0] == '1') ? 1 : 2;   // clusters of 4 do not all fit at once (7.2 M against 9.7 M sims/s)
+        }
         DM_CHECK_ARG((size_t)P0 * H * sizeof(float) <= 200 * 1024, "dm_net_finalize: value head too large");
         {
             const int fs = (int)((size_t)P0 * H * sizeof(float));

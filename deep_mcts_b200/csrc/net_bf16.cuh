@@ -146,6 +146,32 @@ __device__ __forceinline__ u32 umma_desc_lo(u32 saddr, u32 lbo_bytes) {
 __device__ __forceinline__ u32 umma_desc_hi(u32 sbo_bytes) { return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14); }
 __device__ __forceinline__ u64 umma_desc_join(u32 lo, u32 hi) { return (u64)lo | ((u64)hi << 32); }
 
+// ---- thread-block clusters: weight stages multicast to every CTA of a cluster -------------------
+__device__ __forceinline__ u32 cluster_ctarank() {
+    u32 r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {   // every thread of every CTA of the cluster
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy global -> the same shared-memory offset of every CTA in `mask`; each destination CTA's mbarrier (same
+// offset) receives the complete_tx for the bytes that landed in it
+__device__ __forceinline__ void bulk_g2s_multicast(u32 dst, const void* src, u32 bytes, u32 bar, unsigned short mask) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+        : "memory");
+}
+// tcgen05.commit arriving on the mbarrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_multicast(u32 bar, unsigned short mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(mask)
+        : "memory");
+}
+
 // one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
     u32 pred;
@@ -1066,13 +1092,21 @@ inline size_t resblock_smem_bytes() {
     return 1024 + (size_t)2 * kChunks * ResGeom<G>::kWinRows * 16 + (size_t)kStages2 * kStage2Bytes + 512;
 }
 
-template <int G>
-__global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs args) {
+// CL = 2: launched as clusters of two CTAs (one TPC) that walk the weight stream in lockstep -- both run the same
+// number of items -- and share it: each CTA fetches half of every weight stage and multicasts it into both shared
+// memories, so the L2 -> SM weight traffic (4.5x the activation traffic of this kernel) is halved.  A stage is
+// refilled only after the MMAs of BOTH CTAs have released it (multicast tcgen05.commit on a 2-arrival barrier).
+template <int G, int CL = 1>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs args) {
     using Geo = ResGeom<G>;
     extern __shared__ unsigned char smem_raw[];
     const int live = live_count(args.count_dev, args.n_boards);
-    const int n_items = (live + 3) / 4;
+    // CL > 1: rounded up to a whole number of clusters (gridDim.x is one, too), so the CTAs of a cluster run the same
+    // number of items and leave together; an item past the live boards computes on stale rows and stores nothing
+    const int n_items = ((live + 3) / 4 + CL - 1) / CL * CL;
     if ((int)blockIdx.x >= n_items) return;
+    const u32 cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr unsigned short kClusterMask = (unsigned short)((1u << CL) - 1u);
 
     unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
     constexpr u32 kBufBytes = (u32)kChunks * Geo::kWinRows * 16;
@@ -1099,7 +1133,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; ++s) {
             mbar_init(bar_bfull + 8 * s, 1);
-            mbar_init(bar_bempty + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, CL);   // released by the MMA warp of every CTA that reads the stage
         }
         mbar_init(bar_xfull, 1);
         mbar_init(bar_xfree, 1);
@@ -1118,6 +1152,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the zero fill is read by the tensor core
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // the peer's barriers are initialised before anything is multicast at them
     tc_fence_after();
     const u32 tmem_base = *s_tmem;
 
@@ -1139,8 +1174,15 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
 #endif
                         {
                         mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
-                        bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes), w + (size_t)part * kStage2Bytes, kStage2Bytes,
-                                 bar_bfull + 8 * st);
+                        if (CL > 1) {
+                            constexpr u32 kShare = kStage2Bytes / CL;   // this CTA's share of the stage, sent to all
+                            bulk_g2s_multicast(smem_u32(s_b + (size_t)st * kStage2Bytes) + cta_rank * kShare,
+                                               w + (size_t)part * kStage2Bytes + cta_rank * kShare, kShare,
+                                               bar_bfull + 8 * st, kClusterMask);
+                        } else {
+                            bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes), w + (size_t)part * kStage2Bytes, kStage2Bytes,
+                                     bar_bfull + 8 * st);
+                        }
                         }
                     }
                     __syncwarp();
@@ -1214,7 +1256,8 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
                                                 (tap | k16) ? 1u : 0u);
                                 }
                             }
-                            tc_commit(bar_bempty + 8 * st);
+                            if (CL > 1) tc_commit_multicast(bar_bempty + 8 * st, kClusterMask);
+                            else tc_commit(bar_bempty + 8 * st);
                             if (tap == 8 && part == kStagesPerTap - 1) {
                                 if (layer == 0) {
                                     tc_commit(bar_acc1);    // conv1 done: epilogue 1 may start ...
@@ -1345,6 +1388,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_resblock_tc(ResBlockArgs a
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();   // no CTA leaves while a peer may still arrive on its barriers
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
