@@ -61,11 +61,13 @@ def parse_args():
 
 def ncu_dram_traffic_per_launch():
     """dram__bytes_read.sum + dram__bytes_write.sum of the fused residual-block kernel (three blocks per
-    launch) from the committed steady-state `ncu --set full` capture (profiles/r2c_net_kernels_ncu_full_raw.csv,
+    launch) from the committed steady-state `ncu --set full` capture (profiles/r2g_net_kernels_ncu_full_raw.csv,
     Othello 8x8, 4096 games, evaluation cache on: ~3500 live leaves per launch), averaged over the captured
     launches; None if absent."""
     import csv
-    path = ROOT / "profiles" / "r2c_net_kernels_ncu_full_raw.csv"
+    path = ROOT / "profiles" / "r2g_net_kernels_ncu_full_raw.csv"
+    if not path.exists():
+        path = ROOT / "profiles" / "r2c_net_kernels_ncu_full_raw.csv"
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
