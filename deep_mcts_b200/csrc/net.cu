@@ -252,7 +252,12 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const i
     const int conv_blocks = v1 ? (int)(((size_t)n * net->geom.P + netk::kRowsPerCta - 1) / netk::kRowsPerCta)
                                : (conv_items < net->sm_count ? conv_items : net->sm_count);
     const int conv_threads = v1 ? netk::kConvThreads : netk::kConv2Threads;
-    auto conv_kernel = v1 ? netk::k_conv3x3_tc : (pair ? netk::k_conv3x3_tc2<true> : netk::k_conv3x3_tc2<false>);
+    // pair layout: 2-CTA clusters sharing the weight stream (needs an even grid and an even item capacity)
+    const bool conv_cl2 = pair && !v1 && net->trunk_cluster == 2 && conv_blocks >= 2 && (conv_items % 2) == 0;
+    auto conv_kernel = v1 ? netk::k_conv3x3_tc
+                          : (pair ? (conv_cl2 ? netk::k_conv3x3_tc2<true, 2> : netk::k_conv3x3_tc2<true, 1>)
+                                  : netk::k_conv3x3_tc2<false, 1>);
+    const int conv_grid = conv_cl2 ? (conv_blocks & ~1) : conv_blocks;
     netk::ConvArgs a;
     memset(&a, 0, sizeof(a));
     a.rows_total = net->rows_total;
@@ -306,7 +311,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const i
         memcpy(a.bias_c, net->h_trunk_b[2 * i].data(), sizeof(a.bias_c));
         {
             int pc = prof_begin(net, 1, st);
-            conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
+            conv_kernel<<<conv_grid, conv_threads, conv_smem, st>>>(a);
             prof_end(net, pc, st);
         }
         DM_LAUNCH_CHECK();
@@ -319,7 +324,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const i
         }
         {
             int pc = prof_begin(net, 1, st);
-            conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
+            conv_kernel<<<conv_grid, conv_threads, conv_smem, st>>>(a);
             prof_end(net, pc, st);
         }
         DM_LAUNCH_CHECK();
@@ -329,7 +334,7 @@ int run_forward(dm_net* net, int precision, int n, const int* count_dev, const i
     memcpy(a.bias_c, net->h_trunk_b[L - 1].data(), sizeof(a.bias_c));
     {
         int pc = prof_begin(net, 1, st);
-        conv_kernel<<<conv_blocks, conv_threads, conv_smem, st>>>(a);
+        conv_kernel<<<conv_grid, conv_threads, conv_smem, st>>>(a);
         prof_end(net, pc, st);
     }
     DM_LAUNCH_CHECK();
@@ -547,6 +552,8 @@ extern "C" int dm_net_finalize(dm_net* net, void* stream) {
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv2_smem_bytes(net->geom)));
         DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)netk::conv2_smem_bytes_pair()));
+        DM_CUDA(cudaFuncSetAttribute(netk::k_conv3x3_tc2<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::conv2_smem_bytes_pair()));
         DM_CUDA(cudaFuncSetAttribute(netk::k_resblock_tc<8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)netk::resblock_smem_bytes<8>()));

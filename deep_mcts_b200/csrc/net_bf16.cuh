@@ -759,14 +759,20 @@ __global__ void __launch_bounds__(kStemThreads, kStemCtasPerSm) k_stem_tc(StemAr
     }
 }
 
-template <bool kPair>
-__global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args) {
+// CL = 2 (pair layout only): clusters of two CTAs share the weight stream by multicast, exactly as in
+// k_resblock_tc below (same item count per CTA of a cluster, half a stage fetched by each, 2-arrival empty barriers).
+template <bool kPair, int CL = 1>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args) {
+    static_assert(CL == 1 || kPair, "weight-sharing clusters are built for the pair layout");
     extern __shared__ unsigned char smem_raw[];
     const RowGeom geom = args.geom;
     const int a_rows = kPair ? kPairARows : conv2_a_rows(geom);
     const int live = live_count(args.count_dev, args.n_boards);
-    const int n_items = kPair ? (live + 3) / 4 : (int)(((size_t)live * geom.P + kItemRows - 1) / kItemRows);
+    const int n_items = kPair ? ((live + 3) / 4 + CL - 1) / CL * CL   // whole clusters: an item past the live boards stores nothing
+                              : (int)(((size_t)live * geom.P + kItemRows - 1) / kItemRows);
     if ((int)blockIdx.x >= n_items) return;
+    const u32 cta_rank = CL > 1 ? cluster_ctarank() : 0u;
+    constexpr unsigned short kClusterMask = (unsigned short)((1u << CL) - 1u);
 
     unsigned char* base = (unsigned char*)(((size_t)smem_raw + 1023) & ~(size_t)1023);
     const u32 a_buf_bytes = (u32)kChunks * a_rows * 16;
@@ -786,7 +792,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; ++s) {
             mbar_init(bar_bfull + 8 * s, 1);
-            mbar_init(bar_bempty + 8 * s, 1);
+            mbar_init(bar_bempty + 8 * s, CL);
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(bar_afull + 8 * b, 1);
@@ -804,6 +810,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     tc_fence_after();
     const u32 tmem_base = *s_tmem;
 
@@ -816,9 +823,17 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                 if (s >= kStages2) mbar_wait(bar_bempty + 8 * st, ((s / kStages2) - 1) & 1);
                 if (elect_one()) {
                     mbar_expect_tx(bar_bfull + 8 * st, kStage2Bytes);
-                    bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes),
-                             reinterpret_cast<const unsigned char*>(args.w) + (size_t)part * kStage2Bytes, kStage2Bytes,
-                             bar_bfull + 8 * st);
+                    if (CL > 1) {
+                        constexpr u32 kShare = kStage2Bytes / CL;
+                        bulk_g2s_multicast(smem_u32(s_b + (size_t)st * kStage2Bytes) + cta_rank * kShare,
+                                           reinterpret_cast<const unsigned char*>(args.w) + (size_t)part * kStage2Bytes +
+                                               cta_rank * kShare,
+                                           kShare, bar_bfull + 8 * st, kClusterMask);
+                    } else {
+                        bulk_g2s(smem_u32(s_b + (size_t)st * kStage2Bytes),
+                                 reinterpret_cast<const unsigned char*>(args.w) + (size_t)part * kStage2Bytes, kStage2Bytes,
+                                 bar_bfull + 8 * st);
+                    }
                 }
                 __syncwarp();
             }
@@ -882,7 +897,8 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
                                             (tap | k16) ? 1u : 0u);
                             }
                         }
-                        tc_commit(bar_bempty + 8 * st);
+                        if (CL > 1) tc_commit_multicast(bar_bempty + 8 * st, kClusterMask);
+                        else tc_commit(bar_bempty + 8 * st);
                         if (tap == 8 && part == kStagesPerTap - 1) {
                             tc_commit(bar_accfull + 8 * buf);  // accumulators of this item complete
                             tc_commit(bar_aempty + 8 * buf);   // and its activation buffer may be refilled
@@ -998,6 +1014,7 @@ __global__ void __launch_bounds__(kConv2Threads, 1) k_conv3x3_tc2(ConvArgs args)
     }
     tc_fence_before();
     __syncthreads();
+    if (CL > 1) cluster_sync_all();
     if (warp == 1) {
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
